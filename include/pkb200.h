@@ -1,0 +1,215 @@
+/* pkb200.h -- C ABI of the B200-native acoustic front half of pocketkaldi.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int return codes, no
+ * CUDA or torch types. Every entry point names the reference interface it
+ * replaces (paths relative to the pocketkaldi tree). All matrices crossing the
+ * boundary are frame-major float32: element (frame t, dim d) at [t * dim + d],
+ * which is byte-for-byte the reference's column-major pk_matrix_t
+ * {nrow = dim, ncol = frames} (src/matrix.h:19-24, src/matrix.cc:136-144).
+ *
+ * Batches: the reference processes one utterance per call; every batched call
+ * here takes `n_utts` utterances packed back to back with a per-utterance
+ * length array, and n_utts == 1 reproduces the reference call exactly.
+ *
+ * There is no CPU fallback. Every function fails with PKB_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef PKB200_H_
+#define PKB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes (0 == success; message via pkb_last_error) ------------- */
+#define PKB_OK 0
+#define PKB_ERR_INVALID 1     /* bad argument / shape (the reference asserts)       */
+#define PKB_ERR_IO 2          /* reference: Status::IOError   (src/status.h:42)     */
+#define PKB_ERR_CORRUPT 3     /* reference: Status::Corruption (src/status.h:45)    */
+#define PKB_ERR_CUDA 4        /* CUDA runtime / driver failure, or no sm_100 device */
+#define PKB_ERR_UNSUPPORTED 5 /* layer stack outside {Linear,ReLU,Normalize,Softmax} patterns */
+
+/* ---- GEMM arithmetic of the nnet (src/gemm.cc, src/gemm_haswell.cc) ------- */
+#define PKB_PREC_BF16 0   /* one BF16 tcgen05 MMA per product, FP32 accumulate      */
+#define PKB_PREC_BF16X3 1 /* split BF16 (hi+lo), 3 MMAs: FP32-class accuracy; parity mode */
+
+/* ---- fixed front-end geometry (src/fbank.h:7-13, src/cmvn.h:10-11) -------- */
+#define PKB_FBANK_DIM 40
+#define PKB_FRAME_LENGTH 400
+#define PKB_FRAME_SHIFT 160
+#define PKB_CMVN_STATS_DIM 41
+
+typedef struct pkb_ctx pkb_ctx_t;     /* one per GPU: stream, tables, scratch       */
+typedef struct pkb_am pkb_am_t;       /* device-resident AcousticModel              */
+typedef struct pkb_batch pkb_batch_t; /* device-resident utterance batch (pipeline) */
+typedef struct pkb_stream pkb_stream_t; /* streaming state for one audio stream set */
+
+/* Thread-local message of the last failing call on this thread. */
+const char *pkb_last_error(void);
+
+/* Library / build identification: "pkb200 <version> sm_100a". */
+const char *pkb_version(void);
+
+/* ---- context --------------------------------------------------------------*/
+/* Creates the per-GPU context on CUDA device `device` (replaces the table
+ * set-up of Fbank::Fbank, src/fbank.cc:258-265, and pk_srfft_init,
+ * src/srfft.cc:343-356). */
+int pkb_create(int device, pkb_ctx_t **ctx);
+void pkb_destroy(pkb_ctx_t *ctx);
+/* Blocks until all work queued on the context's stream has finished. */
+int pkb_sync(pkb_ctx_t *ctx);
+/* Number of SMs / device name of the context's GPU. */
+int pkb_device_sm_count(pkb_ctx_t *ctx);
+const char *pkb_device_name(pkb_ctx_t *ctx);
+
+/* ---- fbank (Fbank::Compute, src/fbank.cc:267-292) ---------------------------*/
+/* Fbank::CalcNumFrames, src/fbank.cc:35-42. */
+int pkb_fbank_num_frames(int num_samples);
+
+/* wave: all utterances' samples back to back (utterance u starts at
+ * sum(num_samples[0..u-1])), float in int16 range, unscaled, exactly what
+ * pk_16kpcm_read produces (src/pcm_reader.cc:189-211).
+ * feats_out: [sum_u T_u][40] raw log-mel. num_frames_out[u] = T_u (may be NULL). */
+int pkb_fbank_f32(pkb_ctx_t *ctx, const float *wave, const int32_t *num_samples,
+                  int n_utts, float *feats_out, int32_t *num_frames_out);
+/* Same, from 16-bit PCM (skips the float conversion of pcm_reader.cc). */
+int pkb_fbank_i16(pkb_ctx_t *ctx, const int16_t *pcm, const int32_t *num_samples,
+                  int n_utts, float *feats_out, int32_t *num_frames_out);
+
+/* ---- CMVN (CMVN::CMVN + GetFrame for t = 0..T-1, src/cmvn.cc:103-125) -----*/
+/* raw / out: [sum_u T_u][40]; global_stats: 40 sums + count
+ * (the "cmvn_stats" VEC0 of pk_load, src/pocketkaldi.cc:96-104). The float
+ * running sum of ComputeStats (src/cmvn.cc:35-71) is reproduced step by step,
+ * so out equals the reference bit for bit on identical raw input. */
+int pkb_cmvn(pkb_ctx_t *ctx, const float *raw, const int32_t *num_frames, int n_utts,
+             const float *global_stats, float *out);
+
+/* ---- acoustic model (AcousticModel, src/am.h:21-50) -----------------------*/
+/* AcousticModel::Read (src/am.cc:23-63): keys nnet, prior, left_context,
+ * right_context, num_pdfs, tid2pdf of the model .conf; NNT0/LAY0/MAT0/VEC0
+ * readers of src/nnet.cc:80-147, src/matrix.cc:287-319, src/vector.cc:392-425. */
+int pkb_am_load(pkb_ctx_t *ctx, const char *conf_path, int precision, pkb_am_t **am);
+
+/* Same model from memory. layer_types[i] in {0 linear, 1 relu, 2 normalize,
+ * 3 softmax} (src/nnet.h:28-33); for linear layer number j (in order)
+ * weights[j] is W[out][in] row-major as on disk, biases[j] is b[out],
+ * out_dims[j] / in_dims[j] its shape. prior holds probabilities (log is taken
+ * here, as src/am.cc:42-43 does). tid2pdf may be NULL. */
+int pkb_am_create(pkb_ctx_t *ctx, int n_layers, const int32_t *layer_types,
+                  const float *const *weights, const float *const *biases,
+                  const int32_t *out_dims, const int32_t *in_dims, const float *prior,
+                  int num_pdfs, int left_context, int right_context,
+                  const int32_t *tid2pdf, int n_tid2pdf, int precision, pkb_am_t **am);
+void pkb_am_destroy(pkb_am_t *am);
+int pkb_am_num_pdfs(const pkb_am_t *am);        /* AcousticModel::num_pdfs, src/am.h:38 */
+int pkb_am_input_dim(const pkb_am_t *am);       /* nnet input dim = (L+R+1) * feat dim  */
+int pkb_am_left_context(const pkb_am_t *am);
+int pkb_am_right_context(const pkb_am_t *am);
+/* AcousticModel::TransitionIdToPdfId, src/am.h:30-32. -1 when out of range. */
+int pkb_am_tid2pdf(const pkb_am_t *am, int transition_id);
+int pkb_am_num_tids(const pkb_am_t *am);
+
+/* AcousticModel::Compute (src/am.cc:90-115) followed by the decodable's scale
+ * (pk_decodable_init, src/decodable.cc:8-17; pass prob_scale = 1 for the bare
+ * AcousticModel::Compute). feats: [sum_u T_u][feat_dim] CMVN output;
+ * loglik_out: [sum_u T_u][num_pdfs] =
+ *   prob_scale * (log(max(softmax(z), 1e-20)) - log(prior)). */
+int pkb_am_compute(pkb_ctx_t *ctx, pkb_am_t *am, const float *feats,
+                   const int32_t *num_frames, int n_utts, int feat_dim, float prob_scale,
+                   float *loglik_out);
+
+/* Nnet::Propagate (src/nnet.cc:149-163): the layer stack only, no splice, no
+ * prior. in: [rows][in_dim]; out: [rows][out_dim of the last layer]. */
+int pkb_nnet_propagate(pkb_ctx_t *ctx, pkb_am_t *am, const float *in, int rows, int in_dim,
+                       float *out);
+
+/* ---- fused path (the three hot stages of pk_process, src/pocketkaldi.cc:192-216)
+ * 16-bit PCM -> fbank -> CMVN -> splice -> nnet -> scaled log-likelihoods.
+ * feats_out (optional, may be NULL) receives the CMVN features. */
+int pkb_pcm_to_loglik_i16(pkb_ctx_t *ctx, pkb_am_t *am, const int16_t *pcm,
+                          const int32_t *num_samples, int n_utts, const float *global_stats,
+                          float prob_scale, float *loglik_out, float *feats_out,
+                          int32_t *num_frames_out);
+
+/* ---- device-resident batch pipeline ---------------------------------------
+ * The throughput path: buffers live in HBM across calls, nothing is allocated
+ * or copied inside pkb_batch_run. `am` may be NULL for a front-end-only batch. */
+#define PKB_STAGE_FBANK 1
+#define PKB_STAGE_CMVN 2
+#define PKB_STAGE_NNET 4
+#define PKB_STAGE_ALL 7
+
+#define PKB_BUF_PCM 0    /* int16  [sum samples]            */
+#define PKB_BUF_RAW 1    /* float  [frames][40] raw fbank   */
+#define PKB_BUF_FEATS 2  /* float  [frames][40] after CMVN  */
+#define PKB_BUF_LOGLIK 3 /* float  [frames][num_pdfs]       */
+
+int pkb_batch_create(pkb_ctx_t *ctx, pkb_am_t *am, int n_utts, const int32_t *num_samples,
+                     const float *global_stats, float prob_scale, pkb_batch_t **batch);
+void pkb_batch_destroy(pkb_batch_t *batch);
+int64_t pkb_batch_num_frames(const pkb_batch_t *batch);
+int64_t pkb_batch_num_samples(const pkb_batch_t *batch);
+/* Asynchronous host -> device copy of the packed PCM on the context stream. */
+int pkb_batch_set_pcm_i16(pkb_batch_t *batch, const int16_t *pcm);
+/* Fills the PCM buffer on the device with the counter-based synthetic stream
+ * of pocketkaldi_b200/synth.py: utterance u gets id first_utt_id + u. */
+int pkb_batch_synth_pcm(pkb_batch_t *batch, uint64_t seed, uint64_t first_utt_id);
+/* Queues the selected stages on the context stream (asynchronous). */
+int pkb_batch_run(pkb_batch_t *batch, int stages);
+/* Asynchronous device -> host copy of a whole buffer (PKB_BUF_*), or of the
+ * rows [frame0, frame0 + n_frames) of a per-frame buffer. */
+int pkb_batch_get(pkb_batch_t *batch, int which, void *host_dst);
+int pkb_batch_get_rows(pkb_batch_t *batch, int which, int64_t frame0, int64_t n_frames,
+                       void *host_dst);
+/* Sum over all elements of a per-frame float buffer, computed on the device
+ * in double (a cheap whole-output fingerprint for full-size runs). */
+int pkb_batch_checksum(pkb_batch_t *batch, int which, double *sum_out);
+
+/* ---- streaming (carried state; no reference equivalent: the reference has no
+ * streaming API) ---------------------------------------
+ * n_streams concurrent streams advance in lock step, chunk_samples new samples
+ * per stream per call (a multiple of 160). Concatenated outputs equal the
+ * whole-utterance outputs except for the last right_context frames, which are
+ * emitted by pkb_stream_flush. */
+int pkb_stream_create(pkb_ctx_t *ctx, pkb_am_t *am, int n_streams, int chunk_samples,
+                      const float *global_stats, float prob_scale, pkb_stream_t **st);
+void pkb_stream_destroy(pkb_stream_t *st);
+/* pcm: [n_streams][chunk_samples]; loglik_out: [n_streams][max_frames][num_pdfs]
+ * with max_frames = pkb_stream_max_frames(); frames_out = frames produced per
+ * stream by this call (identical for every stream). */
+int pkb_stream_max_frames(const pkb_stream_t *st);
+int pkb_stream_push_i16(pkb_stream_t *st, const int16_t *pcm, float *loglik_out,
+                        int32_t *frames_out);
+int pkb_stream_flush(pkb_stream_t *st, float *loglik_out, int32_t *frames_out);
+
+/* ---- pinned host memory for callers that want overlapped copies ------------*/
+int pkb_host_alloc(void **ptr, uint64_t bytes);
+void pkb_host_free(void *ptr);
+
+/* ---- measurement -----------------------------------------------------------
+ * CUDA events on the context stream (the stream every kernel of this library
+ * is launched on). */
+int pkb_timer_start(pkb_ctx_t *ctx);
+int pkb_timer_stop(pkb_ctx_t *ctx, float *elapsed_ms); /* synchronises */
+/* With profiling on, every kernel launch is bracketed by an event pair and
+ * accumulated per kernel class. */
+#define PKB_KERNEL_FBANK 0
+#define PKB_KERNEL_CMVN 1
+#define PKB_KERNEL_GEMM 2
+#define PKB_KERNEL_FINALIZE 3
+#define PKB_KERNEL_MISC 4
+#define PKB_KERNEL_CLASSES 5
+int pkb_profile_enable(pkb_ctx_t *ctx, int on);
+int pkb_profile_reset(pkb_ctx_t *ctx);
+/* launches[c] / total_ms[c] for c in PKB_KERNEL_*; launches are counted even
+ * with profiling off, times only with it on. */
+int pkb_profile_get(pkb_ctx_t *ctx, int64_t *launches, double *total_ms);
+/* Flushes L2 by writing a scratch buffer larger than the cache. */
+int pkb_flush_l2(pkb_ctx_t *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PKB200_H_ */

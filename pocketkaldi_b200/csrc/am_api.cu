@@ -1,0 +1,629 @@
+// C-ABI entry points of the acoustic model, the device-resident batch pipeline and
+// the model-file readers (AcousticModel::Read, src/am.cc:23-63; Nnet::Read /
+// ReadLayer, src/nnet.cc:80-147; Matrix::Read, src/matrix.cc:287-319; Vector::Read,
+// src/vector.cc:392-425; Configuration::Read, src/configuration.cc:14-71).
+
+#include <ctype.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+
+#include "nnet.cuh"
+
+using pkb::BatchMeta;
+using pkb::Ctx;
+using pkb::InputView;
+using pkb::Workspace;
+
+// ---------------------------------------------------------------- file readers
+namespace {
+
+struct File {
+  FILE *f = nullptr;
+  std::string name;
+  ~File() { if (f) fclose(f); }
+  int open(const std::string &path) {
+    name = path;
+    f = fopen(path.c_str(), "rb");
+    if (!f) {
+      pkb::set_error("IOError: unable to open %s", path.c_str());
+      return PKB_ERR_IO;
+    }
+    return PKB_OK;
+  }
+  int read(void *dst, size_t n) {
+    if (fread(dst, 1, n, f) != n) {
+      pkb::set_error("IOError: failed to read %zu bytes from %s", n, name.c_str());
+      return PKB_ERR_IO;
+    }
+    return PKB_OK;
+  }
+  int expect(const char *tag) {
+    char buf[8] = {0};
+    PKB_TRY(read(buf, 4));
+    if (memcmp(buf, tag, 4) != 0) {
+      pkb::set_error("Corruption: section '%s' expected in %s", tag, name.c_str());
+      return PKB_ERR_CORRUPT;
+    }
+    return PKB_OK;
+  }
+  int read_i32(int32_t *v) { return read(v, 4); }
+};
+
+template <typename T>
+int read_vec(File *fd, std::vector<T> *out) {
+  static_assert(sizeof(T) == 4, "VEC0 payload is 4 bytes per element");
+  int32_t size = 0, dim = 0;
+  PKB_TRY(fd->expect("VEC0"));
+  PKB_TRY(fd->read_i32(&size));
+  PKB_TRY(fd->read_i32(&dim));
+  if (dim < 0 || size != 4 * dim + 4) {
+    pkb::set_error("Corruption: VEC0 section_size = %d * 4 + 4 expected, but %d found: %s", dim, size,
+                   fd->name.c_str());
+    return PKB_ERR_CORRUPT;
+  }
+  out->resize(dim);
+  if (dim) PKB_TRY(fd->read(out->data(), sizeof(T) * dim));
+  return PKB_OK;
+}
+
+int read_mat(File *fd, std::vector<float> *out, int *rows, int *cols) {
+  int32_t size = 0, r = 0, c = 0;
+  PKB_TRY(fd->expect("MAT0"));
+  PKB_TRY(fd->read_i32(&size));
+  if (size != 8) {
+    pkb::set_error("Corruption: MAT0 section_size == 8 expected, but %d found (%s)", size,
+                   fd->name.c_str());
+    return PKB_ERR_CORRUPT;
+  }
+  PKB_TRY(fd->read_i32(&r));
+  PKB_TRY(fd->read_i32(&c));
+  if (r < 0 || c < 0) {
+    pkb::set_error("Corruption: MAT0 negative shape in %s", fd->name.c_str());
+    return PKB_ERR_CORRUPT;
+  }
+  out->resize(static_cast<size_t>(r) * c);
+  std::vector<float> row;
+  for (int i = 0; i < r; ++i) {
+    PKB_TRY(read_vec(fd, &row));
+    if (static_cast<int>(row.size()) != c) {
+      pkb::set_error("Corruption: MAT0 row %d has %zu columns, %d expected (%s)", i, row.size(), c,
+                     fd->name.c_str());
+      return PKB_ERR_CORRUPT;
+    }
+    memcpy(out->data() + static_cast<size_t>(i) * c, row.data(), sizeof(float) * c);
+  }
+  *rows = r;
+  *cols = c;
+  return PKB_OK;
+}
+
+struct HostNnet {
+  std::vector<int32_t> types;
+  std::vector<std::vector<float>> W, b;
+  std::vector<int32_t> out_dims, in_dims;
+};
+
+int read_nnet(const std::string &path, HostNnet *net) {
+  File fd;
+  PKB_TRY(fd.open(path));
+  int32_t size = 0, n = 0;
+  PKB_TRY(fd.expect("NNT0"));
+  PKB_TRY(fd.read_i32(&size));
+  PKB_TRY(fd.read_i32(&n));
+  for (int i = 0; i < n; ++i) {
+    int32_t lsize = 0, type = 0;
+    PKB_TRY(fd.expect("LAY0"));
+    PKB_TRY(fd.read_i32(&lsize));
+    PKB_TRY(fd.read_i32(&type));
+    if (lsize != 4) {
+      pkb::set_error("Corruption: read_layer: section_size == 4 expected, but %d found (%s)", lsize,
+                     path.c_str());
+      return PKB_ERR_CORRUPT;
+    }
+    if (type == 0) {
+      std::vector<float> W, b;
+      int r = 0, c = 0;
+      PKB_TRY(read_mat(&fd, &W, &r, &c));
+      PKB_TRY(read_vec(&fd, &b));
+      if (static_cast<int>(b.size()) != r) {
+        pkb::set_error("Corruption: linear layer: W has %d rows but b has %zu (%s)", r, b.size(),
+                       path.c_str());
+        return PKB_ERR_CORRUPT;
+      }
+      net->W.push_back(std::move(W));
+      net->b.push_back(std::move(b));
+      net->out_dims.push_back(r);
+      net->in_dims.push_back(c);
+    } else if (type < 0 || type > 3) {
+      // the reference reader rejects ADD (4) / MUL (5) as well (src/nnet.cc:122-126)
+      pkb::set_error("Corruption: read_layer: unexpected layer type: %d (%s)", type, path.c_str());
+      return PKB_ERR_CORRUPT;
+    }
+    net->types.push_back(type);
+  }
+  return PKB_OK;
+}
+
+std::string trim(const std::string &s) {
+  size_t a = 0, b = s.size();
+  while (a < b && isspace(static_cast<unsigned char>(s[a]))) ++a;
+  while (b > a && isspace(static_cast<unsigned char>(s[b - 1]))) --b;
+  return s.substr(a, b - a);
+}
+
+int read_conf(const std::string &path, std::map<std::string, std::string> *table) {
+  FILE *f = fopen(path.c_str(), "r");
+  if (!f) {
+    pkb::set_error("IOError: unable to open %s", path.c_str());
+    return PKB_ERR_IO;
+  }
+  char line[4096];
+  int rc = PKB_OK;
+  while (fgets(line, sizeof(line), f)) {
+    std::string s = trim(line);
+    if (s.empty() || s[0] == '#') continue;
+    size_t eq = s.find('=');
+    if (eq == std::string::npos || s.find('=', eq + 1) != std::string::npos) {
+      pkb::set_error("Corruption: Unexpected line in %s: %s", path.c_str(), s.c_str());
+      rc = PKB_ERR_CORRUPT;
+      break;
+    }
+    std::string key = trim(s.substr(0, eq)), val = trim(s.substr(eq + 1));
+    for (auto &ch : key) ch = static_cast<char>(tolower(static_cast<unsigned char>(ch)));
+    if (val.empty()) {
+      pkb::set_error("Corruption: Value cound not be empty: %s", path.c_str());
+      rc = PKB_ERR_CORRUPT;
+      break;
+    }
+    (*table)[key] = val;
+  }
+  fclose(f);
+  return rc;
+}
+
+int conf_get(const std::map<std::string, std::string> &t, const std::string &conf,
+             const char *key, std::string *val) {
+  auto it = t.find(key);
+  if (it == t.end()) {
+    pkb::set_error("Corruption: Unable to find key '%s' in '%s'", key, conf.c_str());
+    return PKB_ERR_CORRUPT;
+  }
+  *val = it->second;
+  return PKB_OK;
+}
+
+std::string conf_path(const std::string &conf, const std::string &v) {
+  if (!v.empty() && v[0] == '/') return v;
+  size_t pos = conf.rfind('/');
+  if (pos == std::string::npos) return v;
+  return conf.substr(0, pos + 1) + v;
+}
+
+int conf_int(const std::map<std::string, std::string> &t, const std::string &conf, const char *key,
+             int *out) {
+  std::string v;
+  PKB_TRY(conf_get(t, conf, key, &v));
+  char *end = nullptr;
+  long x = strtol(v.c_str(), &end, 10);
+  if (end == v.c_str()) {
+    pkb::set_error("Corruption: key '%s' in '%s' is not an integer: %s", key, conf.c_str(), v.c_str());
+    return PKB_ERR_CORRUPT;
+  }
+  *out = static_cast<int>(x);
+  return PKB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- batch object
+struct pkb_batch {
+  Ctx *c = nullptr;
+  pkb_am *am = nullptr;
+  BatchMeta meta;
+  float prob_scale = 1.0f;
+  float global_stats[PKB_CMVN_STATS_DIM];
+  pkb::DevBuf pcm, raw, feats, loglik, sum;
+  Workspace ws;
+  pkb::PaddedPlanes planes;
+  int64_t padded = 0, gemm_rows = 0;
+};
+
+extern "C" {
+
+// ---------------------------------------------------------------- AM
+int pkb_am_create(pkb_ctx_t *c, int n_layers, const int32_t *layer_types,
+                  const float *const *weights, const float *const *biases, const int32_t *out_dims,
+                  const int32_t *in_dims, const float *prior, int num_pdfs, int left_context,
+                  int right_context, const int32_t *tid2pdf, int n_tid2pdf, int precision,
+                  pkb_am_t **am) {
+  return pkb::am_build(c, n_layers, layer_types, weights, biases, out_dims, in_dims, prior, num_pdfs,
+                       left_context, right_context, tid2pdf, n_tid2pdf, precision, am);
+}
+
+int pkb_am_load(pkb_ctx_t *c, const char *conf_file, int precision, pkb_am_t **am) {
+  PKB_REQUIRE(c && conf_file && am, "pkb_am_load: NULL argument");
+  const std::string conf = conf_file;
+  std::map<std::string, std::string> t;
+  PKB_TRY(read_conf(conf, &t));
+  std::string v;
+  HostNnet net;
+  PKB_TRY(conf_get(t, conf, "nnet", &v));
+  PKB_TRY(read_nnet(conf_path(conf, v), &net));
+  std::vector<float> prior;
+  {
+    PKB_TRY(conf_get(t, conf, "prior", &v));
+    File fd;
+    PKB_TRY(fd.open(conf_path(conf, v)));
+    PKB_TRY(read_vec(&fd, &prior));
+  }
+  int left = 0, right = 0, num_pdfs = 0;
+  PKB_TRY(conf_int(t, conf, "left_context", &left));
+  PKB_TRY(conf_int(t, conf, "right_context", &right));
+  PKB_TRY(conf_int(t, conf, "num_pdfs", &num_pdfs));
+  std::vector<int32_t> tid2pdf;
+  {
+    PKB_TRY(conf_get(t, conf, "tid2pdf", &v));
+    File fd;
+    PKB_TRY(fd.open(conf_path(conf, v)));
+    PKB_TRY(read_vec(&fd, &tid2pdf));
+  }
+  if (static_cast<int>(prior.size()) != num_pdfs) {
+    pkb::set_error("Corruption: prior has %zu entries but num_pdfs = %d (%s)", prior.size(), num_pdfs,
+                   conf.c_str());
+    return PKB_ERR_CORRUPT;
+  }
+  std::vector<const float *> W, b;
+  for (size_t i = 0; i < net.W.size(); ++i) {
+    W.push_back(net.W[i].data());
+    b.push_back(net.b[i].data());
+  }
+  return pkb::am_build(c, static_cast<int>(net.types.size()), net.types.data(), W.data(), b.data(),
+                       net.out_dims.data(), net.in_dims.data(), prior.data(), num_pdfs, left, right,
+                       tid2pdf.data(), static_cast<int>(tid2pdf.size()), precision, am);
+}
+
+void pkb_am_destroy(pkb_am_t *am) {
+  if (!am) return;
+  if (am->c) cudaSetDevice(am->c->device);
+  for (auto &st : am->stages) {
+    st.w_hi.release();
+    st.w_lo.release();
+    st.bias.release();
+  }
+  am->splice_stage.w_hi.release();
+  am->splice_stage.w_lo.release();
+  am->splice_stage.bias.release();
+  am->log_prior.release();
+  am->ws.release();
+  am->meta.dev.release();
+  am->in_f32.release();
+  am->out_f32.release();
+  delete am;
+}
+
+int pkb_am_num_pdfs(const pkb_am_t *am) { return am ? am->num_pdfs : 0; }
+int pkb_am_input_dim(const pkb_am_t *am) { return am ? am->input_dim : 0; }
+int pkb_am_left_context(const pkb_am_t *am) { return am ? am->left : 0; }
+int pkb_am_right_context(const pkb_am_t *am) { return am ? am->right : 0; }
+int pkb_am_num_tids(const pkb_am_t *am) { return am ? static_cast<int>(am->tid2pdf.size()) : 0; }
+int pkb_am_tid2pdf(const pkb_am_t *am, int tid) {
+  if (!am || tid < 0 || tid >= static_cast<int>(am->tid2pdf.size())) return -1;
+  return am->tid2pdf[tid];
+}
+
+int pkb_am_compute(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t *num_frames,
+                   int n_utts, int feat_dim, float prob_scale, float *loglik_out) {
+  PKB_REQUIRE(c && am, "pkb_am_compute: NULL argument");
+  PKB_REQUIRE(am->c == c, "pkb_am_compute: model belongs to another context");
+  PKB_REQUIRE(am->has_splice_stage && feat_dim == am->feat_dim,
+              "pkb_am_compute: feat_dim %d does not match the model (nnet input %d, context %d+1+%d)",
+              feat_dim, am->input_dim, am->left, am->right);
+  PKB_CUDA(cudaSetDevice(c->device));
+  BatchMeta &m = am->meta;
+  PKB_TRY(m.build_from_frames(num_frames, n_utts));
+  if (m.total_frames == 0) return PKB_OK;
+  PKB_REQUIRE(feats && loglik_out, "pkb_am_compute: feats / loglik_out is NULL");
+  PKB_TRY(m.upload(c->stream));
+  std::vector<int64_t> pad_off;
+  int64_t padded = 0, rows = 0;
+  pkb::padded_rows(m, am->left, am->right, &pad_off, &padded, &rows);
+  Workspace &ws = am->ws;
+  PKB_TRY(pkb::workspace_ensure(am, &ws, rows));
+  const int dp = am->feat_dim_pad;
+  PKB_TRY(ws.feat_hi.ensure(static_cast<size_t>(padded) * dp * 2));
+  if (am->planes == 2) PKB_TRY(ws.feat_lo.ensure(static_cast<size_t>(padded) * dp * 2));
+  PKB_TRY(ws.pad_off.ensure(pad_off.size() * sizeof(int64_t)));
+  PKB_TRY(ws.row_map.ensure(static_cast<size_t>(rows) * sizeof(int32_t)));
+  PKB_CUDA(cudaMemcpyAsync(ws.pad_off.p, pad_off.data(), pad_off.size() * sizeof(int64_t),
+                           cudaMemcpyHostToDevice, c->stream));
+  const size_t in_bytes = static_cast<size_t>(m.total_frames) * feat_dim * sizeof(float);
+  const size_t out_bytes = static_cast<size_t>(m.total_frames) * am->num_pdfs * sizeof(float);
+  PKB_TRY(am->in_f32.ensure(in_bytes));
+  PKB_TRY(am->out_f32.ensure(out_bytes));
+  PKB_CUDA(cudaMemcpyAsync(am->in_f32.p, feats, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  PKB_CUDA(cudaMemsetAsync(ws.row_map.p, 0xFF, static_cast<size_t>(rows) * sizeof(int32_t), c->stream));
+  __nv_bfloat16 *hi = ws.feat_hi.as<__nv_bfloat16>();
+  __nv_bfloat16 *lo = am->planes == 2 ? ws.feat_lo.as<__nv_bfloat16>() : nullptr;
+  PKB_TRY(pkb::launch_pack_padded(c, am->in_f32.as<float>(), m, feat_dim, dp, am->left, am->right,
+                                  ws.pad_off.as<int64_t>(), hi, lo, ws.row_map.as<int32_t>()));
+  InputView in;
+  in.hi = hi;
+  in.lo = lo;
+  in.rows = rows;
+  in.cols = (am->left + am->right + 1) * dp;
+  in.pitch_elems = dp;
+  PKB_TRY(pkb::nnet_forward(am, &ws, in, &am->splice_stage, true, pkb::kFinalLoglik, prob_scale,
+                            am->out_f32.as<float>(), m.total_frames));
+  PKB_CUDA(cudaMemcpyAsync(loglik_out, am->out_f32.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  PKB_CUDA(cudaStreamSynchronize(c->stream));  // also covers the pad_off staging vector
+  return PKB_OK;
+}
+
+int pkb_nnet_propagate(pkb_ctx_t *c, pkb_am_t *am, const float *in_host, int rows, int in_dim,
+                       float *out) {
+  PKB_REQUIRE(c && am, "pkb_nnet_propagate: NULL argument");
+  PKB_REQUIRE(am->c == c, "pkb_nnet_propagate: model belongs to another context");
+  PKB_REQUIRE(in_dim == am->input_dim, "pkb_nnet_propagate: in_dim %d != nnet input dim %d", in_dim,
+              am->input_dim);
+  PKB_REQUIRE(rows >= 0, "pkb_nnet_propagate: rows < 0");
+  if (rows == 0) return PKB_OK;
+  PKB_REQUIRE(in_host && out, "pkb_nnet_propagate: in / out is NULL");
+  PKB_CUDA(cudaSetDevice(c->device));
+  Workspace &ws = am->ws;
+  PKB_TRY(pkb::workspace_ensure(am, &ws, rows));
+  const int dp = (in_dim + 7) / 8 * 8;
+  const int out_dim = am->stages.back().out_dim;
+  PKB_TRY(ws.feat_hi.ensure(static_cast<size_t>(rows) * dp * 2));
+  if (am->planes == 2) PKB_TRY(ws.feat_lo.ensure(static_cast<size_t>(rows) * dp * 2));
+  const size_t in_bytes = static_cast<size_t>(rows) * in_dim * sizeof(float);
+  const size_t out_bytes = static_cast<size_t>(rows) * out_dim * sizeof(float);
+  PKB_TRY(am->in_f32.ensure(in_bytes));
+  PKB_TRY(am->out_f32.ensure(out_bytes));
+  PKB_CUDA(cudaMemcpyAsync(am->in_f32.p, in_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  __nv_bfloat16 *hi = ws.feat_hi.as<__nv_bfloat16>();
+  __nv_bfloat16 *lo = am->planes == 2 ? ws.feat_lo.as<__nv_bfloat16>() : nullptr;
+  PKB_TRY(pkb::launch_pack_plain(c, am->in_f32.as<float>(), rows, in_dim, dp, hi, lo));
+  InputView in;
+  in.hi = hi;
+  in.lo = lo;
+  in.rows = rows;
+  in.cols = dp;
+  in.pitch_elems = dp;
+  const pkb::FinalMode mode = am->softmax_last ? pkb::kFinalProb : pkb::kFinalRaw;
+  PKB_TRY(pkb::nnet_forward(am, &ws, in, &am->stages[0], false, mode, 1.0f, am->out_f32.as<float>(),
+                            rows));
+  PKB_CUDA(cudaMemcpyAsync(out, am->out_f32.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  PKB_CUDA(cudaStreamSynchronize(c->stream));
+  return PKB_OK;
+}
+
+// ---------------------------------------------------------------- batch pipeline
+int pkb_batch_create(pkb_ctx_t *c, pkb_am_t *am, int n_utts, const int32_t *num_samples,
+                     const float *global_stats, float prob_scale, pkb_batch_t **out) {
+  PKB_REQUIRE(c && out, "pkb_batch_create: NULL argument");
+  PKB_REQUIRE(global_stats, "pkb_batch_create: global_stats is NULL");
+  PKB_REQUIRE(n_utts == 0 || num_samples, "pkb_batch_create: num_samples is NULL");
+  PKB_REQUIRE(!am || am->c == c, "pkb_batch_create: model belongs to another context");
+  PKB_REQUIRE(!am || (am->has_splice_stage && am->feat_dim == pkb::kMel),
+              "pkb_batch_create: the model's feature dim must be %d", pkb::kMel);
+  PKB_CUDA(cudaSetDevice(c->device));
+  std::unique_ptr<pkb_batch> b(new pkb_batch());
+  b->c = c;
+  b->am = am;
+  b->prob_scale = prob_scale;
+  memcpy(b->global_stats, global_stats, sizeof(b->global_stats));
+  int rc = PKB_OK;
+  do {
+    if ((rc = b->meta.build_from_samples(num_samples, n_utts)) != PKB_OK) break;
+    if ((rc = b->meta.upload(c->stream)) != PKB_OK) break;
+    const BatchMeta &m = b->meta;
+    const size_t feat_bytes = static_cast<size_t>(m.total_frames) * pkb::kMel * sizeof(float);
+    if ((rc = b->pcm.ensure(std::max<size_t>(2, static_cast<size_t>(m.total_samples) * 2))) != PKB_OK) break;
+    if ((rc = b->raw.ensure(std::max<size_t>(4, feat_bytes))) != PKB_OK) break;
+    if ((rc = b->feats.ensure(std::max<size_t>(4, feat_bytes))) != PKB_OK) break;
+    if ((rc = b->sum.ensure(sizeof(double))) != PKB_OK) break;
+    if (am) {
+      std::vector<int64_t> pad_off;
+      pkb::padded_rows(m, am->left, am->right, &pad_off, &b->padded, &b->gemm_rows);
+      Workspace &ws = b->ws;
+      if ((rc = pkb::workspace_ensure(am, &ws, b->gemm_rows)) != PKB_OK) break;
+      const int dp = am->feat_dim_pad;
+      const size_t plane_bytes = std::max<size_t>(16, static_cast<size_t>(b->padded) * dp * 2);
+      if ((rc = ws.feat_hi.ensure(plane_bytes)) != PKB_OK) break;
+      if (am->planes == 2 && (rc = ws.feat_lo.ensure(plane_bytes)) != PKB_OK) break;
+      if ((rc = ws.pad_off.ensure(std::max<size_t>(8, pad_off.size() * sizeof(int64_t)))) != PKB_OK) break;
+      if ((rc = ws.row_map.ensure(std::max<size_t>(4, static_cast<size_t>(b->gemm_rows) * 4))) != PKB_OK) break;
+      if ((rc = b->loglik.ensure(std::max<size_t>(4, static_cast<size_t>(m.total_frames) *
+                                                         am->num_pdfs * sizeof(float)))) != PKB_OK)
+        break;
+      if (!pad_off.empty() &&
+          cudaMemcpy(ws.pad_off.p, pad_off.data(), pad_off.size() * sizeof(int64_t),
+                     cudaMemcpyHostToDevice) != cudaSuccess) {
+        pkb::set_error("pkb_batch_create: pad_off upload failed");
+        rc = PKB_ERR_CUDA;
+        break;
+      }
+      // zero the planes once: rows of empty utterances are never written
+      cudaMemsetAsync(ws.feat_hi.p, 0, plane_bytes, c->stream);
+      if (am->planes == 2) cudaMemsetAsync(ws.feat_lo.p, 0, plane_bytes, c->stream);
+      if ((rc = pkb::launch_row_map(c, m, am->left, am->right, ws.pad_off.as<int64_t>(),
+                                    ws.row_map.as<int32_t>(), b->gemm_rows)) != PKB_OK)
+        break;
+      b->planes.hi = ws.feat_hi.as<__nv_bfloat16>();
+      b->planes.lo = am->planes == 2 ? ws.feat_lo.as<__nv_bfloat16>() : nullptr;
+      b->planes.d_pad_off = ws.pad_off.as<int64_t>();
+      b->planes.left = am->left;
+      b->planes.right = am->right;
+      b->planes.dim_pad = dp;
+    }
+    if ((rc = pkb::prepare_cmvn_tables(c, global_stats)) != PKB_OK) break;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      pkb::set_error("pkb_batch_create: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = PKB_ERR_CUDA;
+    }
+  } while (0);
+  if (rc != PKB_OK) {
+    pkb_batch_destroy(b.release());
+    return rc;
+  }
+  *out = b.release();
+  return PKB_OK;
+}
+
+void pkb_batch_destroy(pkb_batch_t *b) {
+  if (!b) return;
+  if (b->c) {
+    cudaSetDevice(b->c->device);
+    cudaStreamSynchronize(b->c->stream);
+  }
+  b->pcm.release();
+  b->raw.release();
+  b->feats.release();
+  b->loglik.release();
+  b->sum.release();
+  b->ws.release();
+  b->meta.dev.release();
+  delete b;
+}
+
+int64_t pkb_batch_num_frames(const pkb_batch_t *b) { return b ? b->meta.total_frames : 0; }
+int64_t pkb_batch_num_samples(const pkb_batch_t *b) { return b ? b->meta.total_samples : 0; }
+
+int pkb_batch_set_pcm_i16(pkb_batch_t *b, const int16_t *pcm) {
+  PKB_REQUIRE(b, "pkb_batch_set_pcm_i16: batch is NULL");
+  if (b->meta.total_samples == 0) return PKB_OK;
+  PKB_REQUIRE(pcm, "pkb_batch_set_pcm_i16: pcm is NULL");
+  PKB_CUDA(cudaMemcpyAsync(b->pcm.p, pcm, static_cast<size_t>(b->meta.total_samples) * 2,
+                           cudaMemcpyHostToDevice, b->c->stream));
+  return PKB_OK;
+}
+
+int pkb_batch_synth_pcm(pkb_batch_t *b, uint64_t seed, uint64_t first_utt_id) {
+  PKB_REQUIRE(b, "pkb_batch_synth_pcm: batch is NULL");
+  return pkb::launch_synth_pcm(b->c, b->pcm.as<int16_t>(), b->meta, seed, first_utt_id);
+}
+
+int pkb_batch_run(pkb_batch_t *b, int stages) {
+  PKB_REQUIRE(b, "pkb_batch_run: batch is NULL");
+  Ctx *c = b->c;
+  if (stages & PKB_STAGE_FBANK)
+    PKB_TRY(pkb::launch_fbank_i16(c, b->pcm.as<int16_t>(), b->meta, b->raw.as<float>()));
+  if (stages & PKB_STAGE_CMVN) {
+    PKB_TRY(pkb::prepare_cmvn_tables(c, b->global_stats));
+    PKB_TRY(pkb::launch_cmvn(c, b->raw.as<float>(), b->meta, b->feats.as<float>(),
+                             b->am ? &b->planes : nullptr));
+  }
+  if (stages & PKB_STAGE_NNET) {
+    PKB_REQUIRE(b->am, "pkb_batch_run: PKB_STAGE_NNET needs a model");
+    pkb_am *am = b->am;
+    InputView in;
+    in.hi = b->planes.hi;
+    in.lo = b->planes.lo;
+    in.rows = b->gemm_rows;
+    in.cols = (am->left + am->right + 1) * am->feat_dim_pad;
+    in.pitch_elems = am->feat_dim_pad;
+    PKB_TRY(pkb::nnet_forward(am, &b->ws, in, &am->splice_stage, true, pkb::kFinalLoglik,
+                              b->prob_scale, b->loglik.as<float>(), b->meta.total_frames));
+  }
+  return PKB_OK;
+}
+
+static int batch_buf(pkb_batch_t *b, int which, char **ptr, size_t *row_bytes, int64_t *rows) {
+  switch (which) {
+    case PKB_BUF_PCM:
+      *ptr = b->pcm.as<char>();
+      *row_bytes = 2;
+      *rows = b->meta.total_samples;
+      return PKB_OK;
+    case PKB_BUF_RAW:
+      *ptr = b->raw.as<char>();
+      *row_bytes = pkb::kMel * sizeof(float);
+      *rows = b->meta.total_frames;
+      return PKB_OK;
+    case PKB_BUF_FEATS:
+      *ptr = b->feats.as<char>();
+      *row_bytes = pkb::kMel * sizeof(float);
+      *rows = b->meta.total_frames;
+      return PKB_OK;
+    case PKB_BUF_LOGLIK:
+      PKB_REQUIRE(b->am, "batch has no model: no log-likelihood buffer");
+      *ptr = b->loglik.as<char>();
+      *row_bytes = static_cast<size_t>(b->am->num_pdfs) * sizeof(float);
+      *rows = b->meta.total_frames;
+      return PKB_OK;
+  }
+  pkb::set_error("unknown buffer id %d", which);
+  return PKB_ERR_INVALID;
+}
+
+int pkb_batch_get_rows(pkb_batch_t *b, int which, int64_t row0, int64_t n_rows, void *host_dst) {
+  PKB_REQUIRE(b, "pkb_batch_get_rows: batch is NULL");
+  char *ptr = nullptr;
+  size_t row_bytes = 0;
+  int64_t rows = 0;
+  PKB_TRY(batch_buf(b, which, &ptr, &row_bytes, &rows));
+  PKB_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= rows,
+              "pkb_batch_get_rows: range [%lld, %lld) outside [0, %lld)", (long long)row0,
+              (long long)(row0 + n_rows), (long long)rows);
+  if (n_rows == 0) return PKB_OK;
+  PKB_REQUIRE(host_dst, "pkb_batch_get_rows: host_dst is NULL");
+  PKB_CUDA(cudaMemcpyAsync(host_dst, ptr + row0 * row_bytes, n_rows * row_bytes,
+                           cudaMemcpyDeviceToHost, b->c->stream));
+  return PKB_OK;
+}
+
+int pkb_batch_get(pkb_batch_t *b, int which, void *host_dst) {
+  PKB_REQUIRE(b, "pkb_batch_get: batch is NULL");
+  char *ptr = nullptr;
+  size_t row_bytes = 0;
+  int64_t rows = 0;
+  PKB_TRY(batch_buf(b, which, &ptr, &row_bytes, &rows));
+  return pkb_batch_get_rows(b, which, 0, rows, host_dst);
+}
+
+int pkb_batch_checksum(pkb_batch_t *b, int which, double *sum_out) {
+  PKB_REQUIRE(b && sum_out, "pkb_batch_checksum: NULL argument");
+  PKB_REQUIRE(which != PKB_BUF_PCM, "pkb_batch_checksum: float buffers only");
+  char *ptr = nullptr;
+  size_t row_bytes = 0;
+  int64_t rows = 0;
+  PKB_TRY(batch_buf(b, which, &ptr, &row_bytes, &rows));
+  const int64_t n = rows * static_cast<int64_t>(row_bytes / sizeof(float));
+  PKB_TRY(pkb::launch_checksum(b->c, reinterpret_cast<const float *>(ptr), n, b->sum.as<double>()));
+  PKB_CUDA(cudaMemcpyAsync(sum_out, b->sum.p, sizeof(double), cudaMemcpyDeviceToHost, b->c->stream));
+  PKB_CUDA(cudaStreamSynchronize(b->c->stream));
+  return PKB_OK;
+}
+
+// ---------------------------------------------------------------- fused host path
+int pkb_pcm_to_loglik_i16(pkb_ctx_t *c, pkb_am_t *am, const int16_t *pcm,
+                          const int32_t *num_samples, int n_utts, const float *global_stats,
+                          float prob_scale, float *loglik_out, float *feats_out,
+                          int32_t *num_frames_out) {
+  PKB_REQUIRE(c && am, "pkb_pcm_to_loglik_i16: NULL argument");
+  pkb_batch_t *b = nullptr;
+  PKB_TRY(pkb_batch_create(c, am, n_utts, num_samples, global_stats, prob_scale, &b));
+  int rc = PKB_OK;
+  do {
+    if (num_frames_out)
+      for (int u = 0; u < n_utts; ++u) num_frames_out[u] = b->meta.num_frames[u];
+    if (b->meta.total_frames == 0) break;
+    if ((rc = pkb_batch_set_pcm_i16(b, pcm)) != PKB_OK) break;
+    if ((rc = pkb_batch_run(b, PKB_STAGE_ALL)) != PKB_OK) break;
+    if (loglik_out && (rc = pkb_batch_get(b, PKB_BUF_LOGLIK, loglik_out)) != PKB_OK) break;
+    if (feats_out && (rc = pkb_batch_get(b, PKB_BUF_FEATS, feats_out)) != PKB_OK) break;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      pkb::set_error("pkb_pcm_to_loglik_i16: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = PKB_ERR_CUDA;
+    }
+  } while (0);
+  pkb_batch_destroy(b);
+  return rc;
+}
+
+}  // extern "C"

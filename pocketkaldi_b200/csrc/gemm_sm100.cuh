@@ -1,0 +1,61 @@
+// Interface of the sm_100a tcgen05 GEMM that replaces pocketkaldi's packed SGEMM
+// (src/gemm.cc:69-304 driver + src/gemm_haswell.cc:72-632 AVX2 6x16 micro-kernel)
+// together with the element-wise layers that follow a LinearLayer
+// (src/nnet.cc:22-75) and the first half of the softmax / AM epilogue
+// (src/vector.cc:264-277, src/am.cc:106-112).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace pkb {
+
+constexpr int kBlockM = 128;   // rows (frames) per CTA tile = TMEM lanes
+constexpr int kBlockK = 64;    // one 128-byte swizzle row of BF16
+constexpr int kUmmaK = 16;     // K of one tcgen05.mma kind::f16
+
+// Epilogue description of one fused GEMM stage:
+//   acc      = A[M x K] * W[N x K]^T                       (FP32 in TMEM)
+//   z        = acc * rowscale(row) + bias[col]             rowscale = sqrt(D / sum_sq(row)) of the
+//                                                          preceding NormalizeLayer, else 1
+//   hidden   : y = relu ? max(z, 0) : z ; optional per-row sum of y^2 (for a following
+//              NormalizeLayer); stored as BF16 hi (+ lo = bf16(y - hi) in BF16X3)
+//   final    : z stored as FP32 at row_map[row] (skipped when < 0) plus per-(row, n-tile)
+//              online-softmax partials (max, sum exp(z - max))
+struct GemmParams {
+  int M;               // rows of A / D
+  int n_tiles_n;       // N_pad / block_n
+  int num_tiles;       // m_tiles * n_tiles_n
+  int num_kb;          // K_pad / kBlockK
+  int N_valid;         // logical N (columns >= N_valid are padding)
+  const float *bias;   // [N_pad], zero in the padding
+  const float *in_sumsq;  // [M][in_sumsq_tiles] partial sums of squares, or nullptr
+  int in_sumsq_tiles;
+  float in_dim;        // D of the NormalizeLayer feeding this stage
+  float *out_sumsq;    // [M][n_tiles_n] or nullptr
+  int relu;
+  __nv_bfloat16 *out_hi, *out_lo;  // [M][ld_out]
+  int ld_out;
+  float *out_f32;      // final: [rows][ld_f32]
+  int ld_f32;
+  const int32_t *row_map;  // final: [M] destination row or -1; nullptr = identity
+  float2 *lse_part;    // final: [M][n_tiles_n], nullptr when no softmax follows
+};
+
+// Encodes a 2-D BF16 K-major tensor map: inner dim `cols` (K), outer dim `rows`,
+// row pitch `pitch_bytes` (may be smaller than cols*2: overlapping rows implement the
+// splice of AcousticModel::SpliceFeats, src/am.cc:65-88), box {64, box_rows}, 128-byte swizzle.
+int make_tensor_map(CUtensorMap *map, const void *base, uint64_t cols, uint64_t rows,
+                    uint64_t pitch_bytes, uint32_t box_rows);
+
+// block_n in {128, 256}; planes in {1 (BF16), 2 (BF16X3)}; final: FP32 output mode.
+int launch_gemm(Ctx *c, int block_n, int planes, bool final, const CUtensorMap *a_hi,
+                const CUtensorMap *a_lo, const CUtensorMap *w_hi, const CUtensorMap *w_lo,
+                const GemmParams &p);
+
+int gemm_max_smem_bytes(int block_n, int planes);
+
+}  // namespace pkb

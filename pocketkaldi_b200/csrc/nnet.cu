@@ -1,0 +1,474 @@
+// Acoustic model on the device: weight packing, the fused layer plan, the forward
+// pass and the small kernels around the GEMMs (pack / row map / finalize).
+//
+// Reference path: AcousticModel::Compute (src/am.cc:90-115) = SpliceFeats (:65-88)
+// -> Nnet::Propagate (src/nnet.cc:149-163: Linear / ReLU / Normalize / Softmax layers,
+// :22-75) -> floor 1e-20, log, minus log-prior (src/am.cc:106-112), then the
+// decodable's prob_scale (src/decodable.cc:15).
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "nnet.cuh"
+
+namespace pkb {
+
+namespace {
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------- kernels
+__global__ void pack_padded_kernel(const float *__restrict__ feats,
+                                   const int64_t *__restrict__ frame_off,
+                                   const int32_t *__restrict__ num_frames,
+                                   const int64_t *__restrict__ pad_off, int n_utts, int dim,
+                                   int dim_pad, int left, int right, int64_t total_frames,
+                                   __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
+                                   int32_t *__restrict__ row_map) {
+  // one thread per (frame, padded column)
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t f = g / dim_pad;
+  const int d = static_cast<int>(g % dim_pad);
+  if (f >= total_frames) return;
+  int a = 0, b = n_utts - 1;
+  while (a < b) {  // largest u with frame_off[u] <= f (utterances with 0 frames are skipped)
+    int mid = (a + b + 1) >> 1;
+    if (frame_off[mid] <= f) a = mid; else b = mid - 1;
+  }
+  const int u = a;
+  const int t = static_cast<int>(f - frame_off[u]);
+  const int T = num_frames[u];
+  const float v = d < dim ? feats[f * dim + d] : 0.0f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  const int64_t base = pad_off[u];
+  const int64_t row = base + left + t;
+  hi[row * dim_pad + d] = h;
+  if (lo) lo[row * dim_pad + d] = l;
+  if (t == 0)
+    for (int r = 0; r < left; ++r) {
+      hi[(base + r) * dim_pad + d] = h;
+      if (lo) lo[(base + r) * dim_pad + d] = l;
+    }
+  if (t == T - 1)
+    for (int r = 0; r < right; ++r) {
+      hi[(row + 1 + r) * dim_pad + d] = h;
+      if (lo) lo[(row + 1 + r) * dim_pad + d] = l;
+    }
+  if (d == 0 && row_map) row_map[base + t] = static_cast<int32_t>(f);
+}
+
+__global__ void row_map_kernel(const int64_t *__restrict__ frame_off,
+                               const int32_t *__restrict__ num_frames,
+                               const int64_t *__restrict__ pad_off, int n_utts,
+                               int32_t *__restrict__ row_map) {
+  const int u = blockIdx.y;
+  if (u >= n_utts) return;
+  const int T = num_frames[u];
+  const int64_t base = pad_off[u], f0 = frame_off[u];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x)
+    row_map[base + t] = static_cast<int32_t>(f0 + t);
+}
+
+__global__ void pack_plain_kernel(const float *__restrict__ in, int64_t rows, int dim, int dim_pad,
+                                  __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t r = g / dim_pad;
+  const int d = static_cast<int>(g % dim_pad);
+  if (r >= rows) return;
+  const float v = d < dim ? in[r * dim + d] : 0.0f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[g] = h;
+  if (lo) lo[g] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// Second half of SoftmaxLayer + AM epilogue + decodable scale. One block per GEMM row.
+//   lse  = log sum_j exp(z_j) from the per-tile (max, sum) partials
+//   prob : exp(z - lse)
+//   ll   : scale * (max(z - lse, log(1e-20f)) - log_prior)     (src/am.cc:106-112,
+//          src/decodable.cc:15; log(max(p, floor)) == max(log p, log floor))
+__global__ void __launch_bounds__(256)
+finalize_kernel(float *__restrict__ out, int ld, int n_valid, const float2 *__restrict__ lse_part,
+                int n_tiles, const int32_t *__restrict__ row_map, int64_t rows, int mode,
+                float scale, float log_floor, const float *__restrict__ log_prior) {
+  for (int64_t m = blockIdx.x; m < rows; m += gridDim.x) {
+    const int64_t dest = row_map ? row_map[m] : m;
+    if (dest < 0) continue;
+    float mx = -INFINITY;
+    for (int i = 0; i < n_tiles; ++i) mx = fmaxf(mx, lse_part[m * n_tiles + i].x);
+    float s = 0.0f;
+    for (int i = 0; i < n_tiles; ++i) {
+      const float2 p = lse_part[m * n_tiles + i];
+      s += p.y * expf(p.x - mx);
+    }
+    const float lse = mx + logf(s);
+    float *row = out + dest * ld;
+    if ((ld & 3) == 0) {
+      float4 *row4 = reinterpret_cast<float4 *>(row);
+      const float4 *lp4 = reinterpret_cast<const float4 *>(log_prior);
+      for (int j = threadIdx.x; j < (n_valid >> 2); j += blockDim.x) {
+        float4 z = row4[j];
+        if (mode == kFinalProb) {
+          z.x = expf(z.x - lse); z.y = expf(z.y - lse); z.z = expf(z.z - lse); z.w = expf(z.w - lse);
+        } else {
+          const float4 lp = lp4[j];
+          z.x = (fmaxf(z.x - lse, log_floor) - lp.x) * scale;
+          z.y = (fmaxf(z.y - lse, log_floor) - lp.y) * scale;
+          z.z = (fmaxf(z.z - lse, log_floor) - lp.z) * scale;
+          z.w = (fmaxf(z.w - lse, log_floor) - lp.w) * scale;
+        }
+        row4[j] = z;
+      }
+      for (int j = (n_valid & ~3) + threadIdx.x; j < n_valid; j += blockDim.x) {
+        const float z = row[j];
+        row[j] = mode == kFinalProb ? expf(z - lse)
+                                    : (fmaxf(z - lse, log_floor) - log_prior[j]) * scale;
+      }
+    } else {
+      for (int j = threadIdx.x; j < n_valid; j += blockDim.x) {
+        const float z = row[j];
+        row[j] = mode == kFinalProb ? expf(z - lse)
+                                    : (fmaxf(z - lse, log_floor) - log_prior[j]) * scale;
+      }
+    }
+  }
+}
+
+__global__ void scale_kernel(float *x, int64_t n, float s) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    x[i] *= s;
+}
+
+// ---------------------------------------------------------------- weight packing
+// W[out][in] float -> BF16 planes [n_pad][k_pad]; column c of the source goes to
+// column remap(c) (identity, or the padded splice layout).
+int pack_stage(Ctx *c, Stage *st, const float *W, const float *b, int out_dim, int in_dim,
+               int group, int group_pad, int planes) {
+  st->in_dim = in_dim;
+  st->out_dim = out_dim;
+  const int groups = group > 0 ? in_dim / group : 1;
+  const int k_logical = group > 0 ? groups * group_pad : in_dim;
+  st->k_pad = round_up(k_logical, kBlockK);
+  const int n128 = round_up(out_dim, 128), n256 = round_up(out_dim, 256);
+  // wide tiles unless they cost more than 6% extra padding
+  st->block_n = (n256 * 100 <= n128 * 106) ? 256 : 128;
+  st->n_pad = st->block_n == 256 ? n256 : n128;
+  const size_t elems = static_cast<size_t>(st->n_pad) * st->k_pad;
+  std::vector<__nv_bfloat16> hi(elems, __float2bfloat16_rn(0.0f)), lo;
+  if (planes == 2) lo.assign(elems, __float2bfloat16_rn(0.0f));
+  for (int o = 0; o < out_dim; ++o) {
+    const float *src = W + static_cast<size_t>(o) * in_dim;
+    __nv_bfloat16 *dh = hi.data() + static_cast<size_t>(o) * st->k_pad;
+    __nv_bfloat16 *dl = planes == 2 ? lo.data() + static_cast<size_t>(o) * st->k_pad : nullptr;
+    for (int k = 0; k < in_dim; ++k) {
+      const int kk = group > 0 ? (k / group) * group_pad + (k % group) : k;
+      const __nv_bfloat16 h = __float2bfloat16_rn(src[k]);
+      dh[kk] = h;
+      if (dl) dl[kk] = __float2bfloat16_rn(src[k] - __bfloat162float(h));
+    }
+  }
+  std::vector<float> bias(st->n_pad, 0.0f);
+  memcpy(bias.data(), b, sizeof(float) * out_dim);
+  PKB_TRY(st->w_hi.ensure(elems * 2));
+  PKB_CUDA(cudaMemcpy(st->w_hi.p, hi.data(), elems * 2, cudaMemcpyHostToDevice));
+  if (planes == 2) {
+    PKB_TRY(st->w_lo.ensure(elems * 2));
+    PKB_CUDA(cudaMemcpy(st->w_lo.p, lo.data(), elems * 2, cudaMemcpyHostToDevice));
+  }
+  PKB_TRY(st->bias.ensure(sizeof(float) * st->n_pad));
+  PKB_CUDA(cudaMemcpy(st->bias.p, bias.data(), sizeof(float) * st->n_pad, cudaMemcpyHostToDevice));
+  PKB_TRY(make_tensor_map(&st->tm_w_hi, st->w_hi.p, st->k_pad, st->n_pad,
+                          static_cast<uint64_t>(st->k_pad) * 2, st->block_n));
+  if (planes == 2)
+    PKB_TRY(make_tensor_map(&st->tm_w_lo, st->w_lo.p, st->k_pad, st->n_pad,
+                            static_cast<uint64_t>(st->k_pad) * 2, st->block_n));
+  else
+    st->tm_w_lo = st->tm_w_hi;
+  (void)c;
+  return PKB_OK;
+}
+
+}  // namespace
+
+void Workspace::release() {
+  for (int i = 0; i < 2; ++i) {
+    act_hi[i].release();
+    act_lo[i].release();
+    sumsq[i].release();
+  }
+  lse_part.release();
+  row_map.release();
+  feat_hi.release();
+  feat_lo.release();
+  pad_off.release();
+}
+
+void padded_rows(const BatchMeta &m, int left, int right, std::vector<int64_t> *pad_off,
+                 int64_t *padded, int64_t *gemm_rows) {
+  pad_off->resize(m.n_utts);
+  const int64_t ctx = left + right;
+  for (int u = 0; u < m.n_utts; ++u) (*pad_off)[u] = m.frame_off[u] + u * ctx;
+  *padded = m.total_frames + static_cast<int64_t>(m.n_utts) * ctx;
+  *gemm_rows = m.total_frames > 0 ? *padded - ctx : 0;
+}
+
+int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *weights,
+             const float *const *biases, const int32_t *out_dims, const int32_t *in_dims,
+             const float *prior, int num_pdfs, int left, int right, const int32_t *tid2pdf,
+             int n_tid2pdf, int precision, pkb_am **out) {
+  PKB_REQUIRE(c && out, "pkb_am_create: NULL argument");
+  PKB_REQUIRE(precision == PKB_PREC_BF16 || precision == PKB_PREC_BF16X3,
+              "pkb_am_create: unknown precision %d", precision);
+  PKB_REQUIRE(left >= 0 && right >= 0, "pkb_am_create: negative context");
+  PKB_REQUIRE(n_layers > 0 && types, "pkb_am_create: empty layer list");
+  PKB_CUDA(cudaSetDevice(c->device));
+  pkb_am *am = new pkb_am();
+  am->c = c;
+  am->precision = precision;
+  am->planes = precision == PKB_PREC_BF16X3 ? 2 : 1;
+  am->left = left;
+  am->right = right;
+  int rc = PKB_OK;
+  int lin = 0;
+  int i = 0;
+  int prev_out = -1;
+  while (i < n_layers && rc == PKB_OK) {
+    if (types[i] != 0) {
+      set_error("layer %d: type %d without a preceding linear layer is not supported", i, types[i]);
+      rc = PKB_ERR_UNSUPPORTED;
+      break;
+    }
+    if (am->softmax_last) {
+      set_error("layer %d: layers after softmax are not supported", i);
+      rc = PKB_ERR_UNSUPPORTED;
+      break;
+    }
+    const int od = out_dims[lin], id = in_dims[lin];
+    if (od <= 0 || id <= 0 || (prev_out >= 0 && id != prev_out)) {
+      set_error("linear layer %d: shape [%d x %d] does not follow output dim %d", lin, od, id,
+                prev_out);
+      rc = PKB_ERR_INVALID;
+      break;
+    }
+    am->stages.emplace_back();
+    Stage &st = am->stages.back();
+    rc = pack_stage(c, &st, weights[lin], biases[lin], od, id, 0, 0, am->planes);
+    if (rc != PKB_OK) break;
+    if (lin == 0) {
+      am->input_dim = id;
+      am->w0_host.assign(weights[0], weights[0] + static_cast<size_t>(od) * id);
+      am->b0_host.assign(biases[0], biases[0] + od);
+    }
+    prev_out = od;
+    ++lin;
+    ++i;
+    if (i < n_layers && types[i] == 1) { st.relu = true; ++i; }
+    if (i < n_layers && types[i] == 2) { st.normalize = true; ++i; }
+    if (i < n_layers && types[i] == 3) { am->softmax_last = true; ++i; }
+    if (i < n_layers && types[i] != 0 && rc == PKB_OK) {
+      set_error("layer %d: type %d in an unsupported position (supported: linear [relu] "
+                "[normalize] ... linear [softmax])", i, types[i]);
+      rc = PKB_ERR_UNSUPPORTED;
+    }
+  }
+  if (rc == PKB_OK) {
+    const Stage &last = am->stages.back();
+    if (last.relu || last.normalize) {
+      set_error("relu / normalize after the last linear layer is not supported");
+      rc = PKB_ERR_UNSUPPORTED;
+    }
+  }
+  if (rc == PKB_OK) {
+    const int outd = am->stages.back().out_dim;
+    am->num_pdfs = num_pdfs > 0 ? num_pdfs : outd;
+    if (prior != nullptr && am->num_pdfs != outd) {
+      set_error("num_pdfs %d != nnet output dim %d", am->num_pdfs, outd);
+      rc = PKB_ERR_INVALID;
+    }
+  }
+  if (rc == PKB_OK) {
+    // log prior: log in double, stored float (src/am.cc:42-43, src/vector.cc:333-339)
+    std::vector<float> lp(am->num_pdfs, 0.0f);
+    if (prior)
+      for (int j = 0; j < am->num_pdfs; ++j) lp[j] = static_cast<float>(log(static_cast<double>(prior[j])));
+    rc = am->log_prior.ensure(sizeof(float) * am->num_pdfs);
+    if (rc == PKB_OK &&
+        cudaMemcpy(am->log_prior.p, lp.data(), sizeof(float) * am->num_pdfs,
+                   cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("log prior upload failed");
+      rc = PKB_ERR_CUDA;
+    }
+  }
+  if (rc == PKB_OK) {
+    const int w = left + right + 1;
+    if (am->input_dim % w == 0) {
+      am->feat_dim = am->input_dim / w;
+      am->feat_dim_pad = round_up(am->feat_dim, 8);  // 16-byte row pitch for the TMA view
+      rc = pack_stage(c, &am->splice_stage, am->w0_host.data(), am->b0_host.data(),
+                      am->stages[0].out_dim, am->input_dim, am->feat_dim, am->feat_dim_pad,
+                      am->planes);
+      if (rc == PKB_OK) {
+        am->splice_stage.relu = am->stages[0].relu;
+        am->splice_stage.normalize = am->stages[0].normalize;
+        am->has_splice_stage = true;
+      }
+    }
+  }
+  if (rc == PKB_OK && tid2pdf && n_tid2pdf > 0) am->tid2pdf.assign(tid2pdf, tid2pdf + n_tid2pdf);
+  if (rc != PKB_OK) {
+    pkb_am_destroy(am);
+    return rc;
+  }
+  *out = am;
+  return PKB_OK;
+}
+
+int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
+  ws->rows = rows;
+  if (rows == 0) return PKB_OK;
+  size_t max_hidden = 0;
+  int max_tiles = 1;
+  const size_t ns = am->stages.size();
+  for (size_t i = 0; i + 1 < ns; ++i) {
+    max_hidden = std::max<size_t>(max_hidden, am->stages[i].n_pad);
+    max_tiles = std::max(max_tiles, am->stages[i].n_pad / am->stages[i].block_n);
+  }
+  const int bufs = ns > 2 ? 2 : (ns > 1 ? 1 : 0);
+  for (int i = 0; i < bufs; ++i) {
+    PKB_TRY(ws->act_hi[i].ensure(static_cast<size_t>(rows) * max_hidden * 2));
+    if (am->planes == 2) PKB_TRY(ws->act_lo[i].ensure(static_cast<size_t>(rows) * max_hidden * 2));
+    PKB_TRY(ws->sumsq[i].ensure(static_cast<size_t>(rows) * max_tiles * sizeof(float)));
+  }
+  const Stage &last = am->stages.back();
+  PKB_TRY(ws->lse_part.ensure(static_cast<size_t>(rows) * (last.n_pad / last.block_n) * sizeof(float2)));
+  return PKB_OK;
+}
+
+int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *first,
+                 bool use_row_map, FinalMode mode, float prob_scale, float *d_out,
+                 int64_t out_rows) {
+  Ctx *c = am->c;
+  const int64_t rows = ws->rows;
+  if (rows == 0) return PKB_OK;
+  PKB_REQUIRE(rows <= INT32_MAX, "nnet_forward: %lld rows exceed the 2^31 limit of one launch",
+              static_cast<long long>(rows));
+  PKB_REQUIRE(in.rows == rows, "nnet_forward: input rows %lld != workspace rows %lld",
+              static_cast<long long>(in.rows), static_cast<long long>(rows));
+  const size_t ns = am->stages.size();
+  const __nv_bfloat16 *a_hi = in.hi, *a_lo = in.lo;
+  int a_cols = in.cols, a_pitch = in.pitch_elems;
+  const float *in_sumsq = nullptr;
+  int in_sumsq_tiles = 0;
+  float in_dim = 0.0f;
+  const int m_tiles = static_cast<int>((rows + kBlockM - 1) / kBlockM);
+  for (size_t i = 0; i < ns; ++i) {
+    const Stage &st = i == 0 ? *first : am->stages[i];
+    const bool final = i + 1 == ns;
+    CUtensorMap tm_a_hi, tm_a_lo;
+    PKB_TRY(make_tensor_map(&tm_a_hi, a_hi, a_cols, rows, static_cast<uint64_t>(a_pitch) * 2, kBlockM));
+    if (am->planes == 2)
+      PKB_TRY(make_tensor_map(&tm_a_lo, a_lo, a_cols, rows, static_cast<uint64_t>(a_pitch) * 2, kBlockM));
+    else
+      tm_a_lo = tm_a_hi;
+    GemmParams p{};
+    p.M = static_cast<int>(rows);
+    p.n_tiles_n = st.n_pad / st.block_n;
+    const int64_t tiles = static_cast<int64_t>(m_tiles) * p.n_tiles_n;
+    PKB_REQUIRE(tiles <= INT32_MAX, "nnet_forward: too many tiles");
+    p.num_tiles = static_cast<int>(tiles);
+    p.num_kb = st.k_pad / kBlockK;
+    p.N_valid = st.out_dim;
+    p.bias = st.bias.as<float>();
+    p.in_sumsq = in_sumsq;
+    p.in_sumsq_tiles = in_sumsq_tiles;
+    p.in_dim = in_dim;
+    p.relu = st.relu ? 1 : 0;
+    if (!final) {
+      const int buf = static_cast<int>(i & 1);
+      p.out_hi = ws->act_hi[buf].as<__nv_bfloat16>();
+      p.out_lo = am->planes == 2 ? ws->act_lo[buf].as<__nv_bfloat16>() : nullptr;
+      p.ld_out = st.n_pad;
+      p.out_sumsq = st.normalize ? ws->sumsq[buf].as<float>() : nullptr;
+    } else {
+      p.out_f32 = d_out;
+      p.ld_f32 = st.out_dim;
+      p.row_map = use_row_map ? ws->row_map.as<int32_t>() : nullptr;
+      p.lse_part = (am->softmax_last && mode != kFinalRaw) ? ws->lse_part.as<float2>() : nullptr;
+    }
+    PKB_TRY(launch_gemm(c, st.block_n, am->planes, final, &tm_a_hi, &tm_a_lo, &st.tm_w_hi,
+                        &st.tm_w_lo, p));
+    if (!final) {
+      a_hi = p.out_hi;
+      a_lo = p.out_lo;
+      a_cols = st.n_pad;
+      a_pitch = st.n_pad;
+      in_sumsq = p.out_sumsq;
+      in_sumsq_tiles = p.n_tiles_n;
+      in_dim = static_cast<float>(st.out_dim);
+    } else if (p.lse_part != nullptr) {
+      const float log_floor = static_cast<float>(log(static_cast<double>(static_cast<float>(1.0e-20))));
+      const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(c->sm_count) * 16));
+      LaunchScope scope(c, PKB_KERNEL_FINALIZE);
+      finalize_kernel<<<grid, 256, 0, c->stream>>>(d_out, st.out_dim, st.out_dim, p.lse_part,
+                                                   p.n_tiles_n, p.row_map, rows, mode, prob_scale,
+                                                   log_floor, am->log_prior.as<float>());
+      PKB_CUDA(cudaGetLastError());
+    } else if (prob_scale != 1.0f && mode == kFinalLoglik) {
+      const int64_t n = out_rows * st.out_dim;
+      const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(c->sm_count) * 8));
+      LaunchScope scope(c, PKB_KERNEL_FINALIZE);
+      scale_kernel<<<grid, 256, 0, c->stream>>>(d_out, n, prob_scale);
+      PKB_CUDA(cudaGetLastError());
+    }
+  }
+  return PKB_OK;
+}
+
+int launch_pack_padded(Ctx *c, const float *d_feats, const BatchMeta &m, int dim, int dim_pad,
+                       int left, int right, const int64_t *d_pad_off, __nv_bfloat16 *hi,
+                       __nv_bfloat16 *lo, int32_t *row_map) {
+  if (m.total_frames == 0) return PKB_OK;
+  const int64_t threads = m.total_frames * dim_pad;
+  const int grid = static_cast<int>((threads + 255) / 256);
+  LaunchScope scope(c, PKB_KERNEL_MISC);
+  pack_padded_kernel<<<grid, 256, 0, c->stream>>>(d_feats, m.d_frame_off, m.d_num_frames, d_pad_off,
+                                                  m.n_utts, dim, dim_pad, left, right,
+                                                  m.total_frames, hi, lo, row_map);
+  PKB_CUDA(cudaGetLastError());
+  return PKB_OK;
+}
+
+int launch_pack_plain(Ctx *c, const float *d_in, int64_t rows, int dim, int dim_pad,
+                      __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
+  if (rows == 0) return PKB_OK;
+  const int64_t threads = rows * dim_pad;
+  const int grid = static_cast<int>((threads + 255) / 256);
+  LaunchScope scope(c, PKB_KERNEL_MISC);
+  pack_plain_kernel<<<grid, 256, 0, c->stream>>>(d_in, rows, dim, dim_pad, hi, lo);
+  PKB_CUDA(cudaGetLastError());
+  return PKB_OK;
+}
+
+int launch_row_map(Ctx *c, const BatchMeta &m, int left, int right, const int64_t *d_pad_off,
+                   int32_t *row_map, int64_t rows) {
+  (void)left;
+  (void)right;
+  if (rows == 0) return PKB_OK;
+  PKB_CUDA(cudaMemsetAsync(row_map, 0xFF, static_cast<size_t>(rows) * sizeof(int32_t), c->stream));
+  int max_t = 0;
+  for (int32_t t : m.num_frames) max_t = std::max(max_t, t);
+  const int bx = std::max(1, std::min((max_t + 255) / 256, 16));
+  for (int u0 = 0; u0 < m.n_utts; u0 += 32768) {
+    const int nu = std::min(32768, m.n_utts - u0);
+    LaunchScope scope(c, PKB_KERNEL_MISC);
+    row_map_kernel<<<dim3(bx, nu), 256, 0, c->stream>>>(m.d_frame_off + u0, m.d_num_frames + u0,
+                                                        d_pad_off + u0, nu, row_map);
+    PKB_CUDA(cudaGetLastError());
+  }
+  return PKB_OK;
+}
+
+}  // namespace pkb

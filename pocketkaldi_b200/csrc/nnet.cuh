@@ -1,0 +1,106 @@
+// Device-resident acoustic model and the fused forward pass.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+
+namespace pkb {
+
+// One LinearLayer with the element-wise layers fused behind it.
+struct Stage {
+  int in_dim = 0, out_dim = 0;  // logical K, N
+  int k_pad = 0, n_pad = 0;     // K padded to 64, N padded to block_n
+  int block_n = 128;
+  bool relu = false;            // ReLULayer follows       (src/nnet.cc:49-60)
+  bool normalize = false;       // NormalizeLayer follows  (src/nnet.cc:62-75)
+  DevBuf w_hi, w_lo, bias;      // [n_pad][k_pad] BF16 planes, [n_pad] FP32
+  CUtensorMap tm_w_hi, tm_w_lo;
+};
+
+// How the final stage's logits are turned into the caller's output.
+enum FinalMode {
+  kFinalRaw = 0,     // z                                   (stack without SoftmaxLayer)
+  kFinalProb = 1,    // softmax(z)                          (Nnet::Propagate, src/nnet.cc:149-163)
+  kFinalLoglik = 2,  // s*(log(max(softmax(z),1e-20))-lp)   (AcousticModel::Compute + decodable scale)
+};
+
+// A [rows][cols] BF16 matrix (one or two planes) as the first GEMM's A operand.
+// pitch_elems < cols describes overlapping rows (the splice view).
+struct InputView {
+  const __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+  int64_t rows = 0;
+  int cols = 0;
+  int pitch_elems = 0;
+};
+
+// Per-batch scratch of the forward pass.
+struct Workspace {
+  int64_t rows = 0;  // M of every GEMM
+  DevBuf act_hi[2], act_lo[2], sumsq[2], lse_part, row_map;
+  // padded feature planes of the batch pipeline
+  DevBuf feat_hi, feat_lo, pad_off;
+  void release();
+};
+
+}  // namespace pkb
+
+struct pkb_am {
+  pkb::Ctx *c = nullptr;
+  int precision = PKB_PREC_BF16;
+  int planes = 1;
+  int left = 0, right = 0, num_pdfs = 0;
+  int input_dim = 0;   // nnet input dim
+  int feat_dim = 0;    // input_dim / (left + right + 1) when divisible, else 0
+  int feat_dim_pad = 0;
+  bool softmax_last = false;
+  std::vector<pkb::Stage> stages;
+  // stage 0 weights re-laid for the padded splice view (feat_dim_pad per context frame);
+  // identical to stages[0] when feat_dim % 8 == 0
+  pkb::Stage splice_stage;
+  bool has_splice_stage = false;
+  pkb::DevBuf log_prior;  // [num_pdfs], log taken at load (src/am.cc:42-43)
+  std::vector<int32_t> tid2pdf;
+  // host copies kept for building splice_stage
+  std::vector<float> w0_host, b0_host;
+  // scratch of the synchronous host-buffer entry points (pkb_am_compute, pkb_nnet_propagate)
+  pkb::Workspace ws;
+  pkb::BatchMeta meta;
+  pkb::DevBuf in_f32, out_f32;
+};
+
+namespace pkb {
+
+int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *weights,
+             const float *const *biases, const int32_t *out_dims, const int32_t *in_dims,
+             const float *prior, int num_pdfs, int left, int right, const int32_t *tid2pdf,
+             int n_tid2pdf, int precision, pkb_am **out);
+
+// Sizes `ws` for `rows` GEMM rows of model `am`.
+int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows);
+
+// Runs every stage. `first` selects the weights of stage 0 (am->stages[0] or
+// am->splice_stage). Output rows are scattered through ws->row_map when
+// use_row_map (padded batch), else written 1:1.
+int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *first,
+                 bool use_row_map, FinalMode mode, float prob_scale, float *d_out, int64_t out_rows);
+
+// float [F][dim] -> padded BF16 planes with replicated edge frames + row map.
+int launch_pack_padded(Ctx *c, const float *d_feats, const BatchMeta &m, int dim, int dim_pad,
+                       int left, int right, const int64_t *d_pad_off, __nv_bfloat16 *hi,
+                       __nv_bfloat16 *lo, int32_t *row_map);
+// float [rows][dim] -> BF16 planes [rows][dim_pad] (zero padded columns).
+int launch_pack_plain(Ctx *c, const float *d_in, int64_t rows, int dim, int dim_pad,
+                      __nv_bfloat16 *hi, __nv_bfloat16 *lo);
+// row_map for a padded batch without packing (the CMVN kernel wrote the planes).
+int launch_row_map(Ctx *c, const BatchMeta &m, int left, int right, const int64_t *d_pad_off,
+                   int32_t *row_map, int64_t rows);
+
+// Padded-row bookkeeping: pad_off[u] = frame_off[u] + u*(left+right); returns total padded
+// rows and the GEMM row count (padded rows - (left+right), 0 for an empty batch).
+void padded_rows(const BatchMeta &m, int left, int right, std::vector<int64_t> *pad_off,
+                 int64_t *padded, int64_t *gemm_rows);
+
+}  // namespace pkb

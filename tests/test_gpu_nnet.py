@@ -1,0 +1,139 @@
+"""GPU parity of the nnet / acoustic-model path (tcgen05 GEMMs + fused epilogues) through the
+C ABI, against the compiled-reference golden vectors and the restatement oracle."""
+
+import numpy as np
+import pytest
+
+import pocketkaldi_b200 as pk
+from pocketkaldi_b200 import formats
+from pocketkaldi_b200.synth import synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+LL_TOL = 2e-2        # north_star: log-likelihoods within 2e-2 absolute
+ARGMAX_MIN = 0.999   # north_star: per-frame argmax pdf agreement
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pk.Context(0)
+    yield c
+    c.close()
+
+
+def toy_layers(toy_conf):
+    conf = formats.read_conf(toy_conf)
+    layers = formats.read_nnet(formats.conf_path(toy_conf, conf["nnet"]))
+    prior = formats.read_vector(formats.conf_path(toy_conf, conf["prior"]))
+    return conf, layers, prior
+
+
+def test_nnet_known_answers(ctx, golden):
+    # test/nnet_test.cc:23-73 (Linear 3->4 and Softmax known answers; tolerance of the
+    # split-BF16 path is 1e-5 instead of the reference's FP32 1e-6)
+    W, b, x = golden["nnet_kat_W"], golden["nnet_kat_b"], golden["nnet_kat_x"]
+    y = pk.Nnet(ctx).from_layers([("linear", W, b)]).Propagate(x)
+    assert np.max(np.abs(y - golden["nnet_kat_linear_y"])) < 1e-5
+    eye = np.eye(4, dtype=np.float32)
+    z = np.zeros(4, np.float32)
+    ys = pk.Nnet(ctx).from_layers([("linear", eye, z), ("softmax",)]).Propagate(golden["nnet_kat_x4"])
+    assert np.max(np.abs(ys - golden["nnet_kat_softmax_y"])) < 1e-5
+    # ReLU and Normalize are only reachable fused behind a linear layer
+    yr = pk.Nnet(ctx).from_layers([("linear", eye, z), ("relu",), ("linear", eye, z)]).Propagate(golden["nnet_kat_x4"])
+    assert np.max(np.abs(yr - golden["nnet_kat_relu_y"])) < 1e-5
+    yn = pk.Nnet(ctx).from_layers([("linear", eye, z), ("normalize",), ("linear", eye, z)]).Propagate(golden["nnet_kat_x4"])
+    assert abs(float((yn.astype(np.float64) ** 2).sum()) - 4.0) < 1e-4
+
+
+@pytest.mark.parametrize("m,n,k", [(512, 512, 512), (100, 100, 1), (1, 1, 1), (121, 233, 17),
+                                   (300, 3000, 1024), (1000, 1024, 440)])
+def test_gemm_differential(ctx, oracle, m, n, k):
+    # test/gemm_test.cc:32-62 shapes (+ the config-3 layer shapes): linear layer vs the oracle
+    rng = np.random.default_rng(m + n + k)
+    A = rng.random((m, k), dtype=np.float32)
+    W = rng.random((n, k), dtype=np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T + b
+    y3 = pk.Nnet(ctx, pk.PREC_BF16X3).from_layers([("linear", W, b)]).Propagate(A)
+    assert y3.shape == (m, n)
+    assert np.max(np.abs(y3 - ref) / np.maximum(1.0, np.abs(ref))) < 2e-5
+    y1 = pk.Nnet(ctx, pk.PREC_BF16).from_layers([("linear", W, b)]).Propagate(A)
+    assert np.max(np.abs(y1 - ref) / np.maximum(1.0, np.abs(ref))) < 1e-2
+    if m * n * k <= 512 ** 3:
+        yo = oracle.linear(A, W, b)
+        assert np.max(np.abs(y3 - yo) / np.maximum(1.0, np.abs(yo))) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["hello", "cat", "noise10"])
+def test_am_loglik_vs_reference_golden(ctx, golden, toy_conf, name):
+    am = pk.AcousticModel(ctx, pk.PREC_BF16X3).Read(toy_conf)
+    assert am.num_pdfs() == 12
+    ll = am.Compute(golden[name + "_cmvn_ref"])
+    ref = golden[name + "_toy_loglik_ref"]
+    assert ll.shape == ref.shape
+    assert np.max(np.abs(ll - ref)) < LL_TOL
+    assert np.mean(ll.argmax(1) == ref.argmax(1)) >= ARGMAX_MIN
+
+
+def test_decodable_vs_reference_golden(ctx, golden, toy_conf):
+    am = pk.AcousticModel(ctx, pk.PREC_BF16X3).Read(toy_conf)
+    d = pk.Decodable(am, 0.1, golden["hello_cmvn_ref"])
+    ref = golden["hello_toy_decodable_ref"]
+    got = np.array([[d.loglikelihood(t, tid) for tid in range(1, 25)] for t in range(ref.shape[0])],
+                   np.float32)
+    assert np.max(np.abs(got - ref)) < LL_TOL * 0.1
+    assert [d.islastframe(t) for t in range(ref.shape[0])] == [bool(v) for v in golden["hello_toy_islast_ref"]]
+    assert am.TransitionIdToPdfId(3) == 1 and am.TransitionIdToPdfId(9999) == -1
+
+
+def test_am_batch_ragged_matches_single(ctx, golden, toy_conf, oracle):
+    conf, layers, prior = toy_layers(toy_conf)
+    am = pk.AcousticModel(ctx, pk.PREC_BF16X3).Read(toy_conf)
+    rng = np.random.default_rng(4)
+    feats = [(rng.standard_normal((n, 40)) * 2.5).astype(np.float32) for n in (1, 0, 7, 130, 3, 257)]
+    outs = am.compute_batch(feats)
+    for f, o in zip(feats, outs):
+        assert o.shape == (f.shape[0], 12)
+        if f.shape[0]:
+            ref = oracle.am_compute(f, layers, prior, 5, 5)
+            assert np.max(np.abs(o - ref)) < LL_TOL
+            assert np.array_equal(o, am.Compute(f))
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_mid_size_dnn_vs_oracle(ctx, oracle, normalize):
+    # 440 -> 3 x 256 -> 1000, random init (SURVEY.md 8d distribution), 600 frames, ragged batch
+    rng = np.random.default_rng(11)
+    layers = formats.make_dnn(rng, 440, 256, 3, 1000, normalize=normalize)
+    prior = np.full(1000, 1e-3, np.float32)
+    feats = [(rng.standard_normal((n, 40)) * 2.5).astype(np.float32) for n in (250, 350)]
+    ref = [oracle.am_compute(f, layers, prior, 5, 5) for f in feats]
+    am3 = pk.AcousticModel(ctx, pk.PREC_BF16X3).from_layers(layers, prior, 5, 5)
+    for o, r in zip(am3.compute_batch(feats), ref):
+        assert np.max(np.abs(o - r)) < LL_TOL
+        assert np.mean(o.argmax(1) == r.argmax(1)) >= ARGMAX_MIN
+    # plain BF16 (throughput mode): looser, reported rather than gated at the parity bar
+    am1 = pk.AcousticModel(ctx, pk.PREC_BF16).from_layers(layers, prior, 5, 5)
+    for o, r in zip(am1.compute_batch(feats), ref):
+        assert np.max(np.abs(o - r)) < 0.5
+        assert np.mean(o.argmax(1) == r.argmax(1)) >= 0.9
+
+
+def test_fused_pcm_to_loglik(ctx, golden, toy_conf):
+    am = pk.AcousticModel(ctx, pk.PREC_BF16X3).Read(toy_conf)
+    pcms = [golden["hello_pcm"], golden["cat_pcm"], synth_pcm(1234, [0], 160000)[0],
+            np.zeros(100, np.int16)]
+    lls, feats = am.pcm_to_loglik(pcms, golden["cmvn_stats"], 1.0, want_feats=True)
+    for name, ll, ft in zip(["hello", "cat", "noise10"], lls, feats):
+        assert np.max(np.abs(ft - golden[name + "_cmvn_ref"]) /
+                      np.maximum(1.0, np.abs(golden[name + "_cmvn_ref"]))) < 1e-4
+        ref = golden[name + "_toy_loglik_ref"]
+        assert np.max(np.abs(ll - ref)) < LL_TOL
+        assert np.mean(ll.argmax(1) == ref.argmax(1)) >= ARGMAX_MIN
+    assert lls[3].shape == (0, 12)
+
+
+def test_unsupported_stack_is_an_error(ctx):
+    with pytest.raises(pk.PkbError) as e:
+        pk.Nnet(ctx).from_layers([("relu",), ("linear", np.eye(4, dtype=np.float32), np.zeros(4, np.float32))])
+    assert e.value.code == 5

@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""Benchmark of the acoustic front half: 16 kHz PCM -> fbank -> CMVN -> nnet log-likelihoods.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE
+JSON line on rank 0. A "step" is one pass of the hot path over one resident batch of synthetic
+utterances. Default workload = BASELINE.json configs[2]: 4096 utterances x 10 s, splice +-5 ->
+6 x 1024 ReLU DNN -> 3000 pdfs, BF16 tensor-core path, per GPU (weak scaling: every rank
+processes its own 4096 utterances, no data-path collective; torch.distributed is used for the
+barrier and the max-over-ranks time only).
+
+  value      frames/s with PCM already resident in HBM, CUDA events on the library's stream
+  e2e        the same through the host-buffer API: pinned PCM H2D + compute + log-likelihood D2H
+  roofline   dominant kernel (tcgen05 GEMM): algorithmic FLOPs / summed CUDA-event time of the
+             GEMM launches in the timed region, against MEASURED_PEAKS.json
+  cpu_baseline  the unmodified reference (oracle/_ref) timed on this host's cores (N=1 only)
+
+`--impl reference` times the reference's own CPU path (all host threads) on the same config.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "acoustic frames/s (fbank+CMVN+nnet loglik)"
+SAMPLES_10S = 160000
+FRAMES_10S = 998
+
+CONFIGS = {
+    # name: (utts per GPU, hidden layers, width, pdfs, nnet?)
+    "2": dict(utts=360, hidden=0, width=0, pdfs=0, nnet=False,
+              name="config2: 1 h of 16 kHz audio in 10 s utterances, 40-dim fbank + CMVN only"),
+    "3": dict(utts=4096, hidden=6, width=1024, pdfs=3000, nnet=True,
+              name="config3: 4096 utts x 10 s, splice+-5 -> 6x1024 ReLU DNN -> 3000 pdfs"),
+    "4": dict(utts=1024, hidden=7, width=2048, pdfs=8000, nnet=True,
+              name="config4 shard: 1024 utts x 10 s per GPU, splice+-5 -> 7x2048 ReLU DNN -> 8000 pdfs"),
+}
+
+
+def flops_per_frame(cfg):
+    if not cfg["nnet"]:
+        return 0
+    h, w, p = cfg["hidden"], cfg["width"], cfg["pdfs"]
+    return 2 * (440 * w + (h - 1) * w * w + w * p)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"],
+                    tensor_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+def make_layers(cfg, seed=0):
+    from pocketkaldi_b200 import formats
+    rng = np.random.default_rng(seed)
+    return formats.make_dnn(rng, 440, cfg["width"], cfg["hidden"], cfg["pdfs"])
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(prefix="pkb_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            # median of the samples taken under load (upper half)
+            top = sorted(sm)[len(sm) // 2:]
+            out["sm_mhz"] = float(np.median(top))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(dist, local, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(dist, local, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ----------------------------------------------------------------------------- reference arm
+def write_reference_model(cfg, tmpdir):
+    from pocketkaldi_b200 import formats
+    from pocketkaldi_b200.synth import synth_global_cmvn
+    layers = make_layers(cfg)
+    prior = np.full(cfg["pdfs"], 1.0 / cfg["pdfs"], np.float32)
+    tid2pdf = np.arange(-1, cfg["pdfs"], dtype=np.int32)
+    tid2pdf[0] = 0
+    return formats.write_model_dir(tmpdir, "bench", layers, prior, 5, 5, tid2pdf,
+                                   cmvn_stats=synth_global_cmvn()), layers, prior
+
+
+def time_reference(cfg, n_threads, n_utts, repeats):
+    """Times the unmodified reference (oracle/_ref) on n_utts synthetic utterances."""
+    from oracle.oracle import Reference
+    from pocketkaldi_b200.synth import synth_pcm, synth_global_cmvn
+    ref = Reference()
+    g = synth_global_cmvn()
+    pcm = synth_pcm(1234, np.arange(n_utts), SAMPLES_10S)
+    am = None
+    tmp = None
+    if cfg["nnet"]:
+        tmp = tempfile.TemporaryDirectory(prefix="pkb_bench_model_")
+        conf, _, _ = write_reference_model(cfg, tmp.name)
+        am = ref.am_load(conf)
+    sec, frames, chk = ref.time_path(am, g, pcm, n_threads, repeats)
+    if am:
+        ref.am_free(am)
+    if tmp:
+        tmp.cleanup()
+    return sec, frames, chk
+
+
+def reference_sample_size(cfg, cores):
+    # ~1.2 s per 10 s utterance per thread for the config-3 net, ~6 s for config 4
+    if not cfg["nnet"]:
+        return max(64, 16 * cores)
+    return max(cores, 8) if cfg["width"] <= 1024 else cores
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_utts = reference_sample_size(cfg, cores)
+    times = []
+    frames = 0
+    for i in range(args.warmup + args.steps):
+        sec, frames, _ = time_reference(cfg, cores, n_utts, 1)
+        if i >= args.warmup:
+            times.append(sec)
+    total = float(sum(times))
+    value = frames * len(times) / total
+    sample = "%d synthetic 10 s utterances (%d frames) per step, %d host threads, oracle/_ref" % (
+        n_utts, frames, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rtfx": value / 100.0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args, cfg):
+    import pocketkaldi_b200 as pk
+    from pocketkaldi_b200.binding import PinnedArray
+    from pocketkaldi_b200.synth import synth_global_cmvn, synth_pcm
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    peaks = load_peaks()
+    ctx = pk.Context(local)
+    g = synth_global_cmvn()
+    prec = pk.PREC_BF16X3 if args.precision == "bf16x3" else pk.PREC_BF16
+    n_utts = args.utts or cfg["utts"]
+    am = None
+    layers = prior = None
+    if cfg["nnet"]:
+        layers = make_layers(cfg)
+        prior = np.full(cfg["pdfs"], 1.0 / cfg["pdfs"], np.float32)
+        am = pk.AcousticModel(ctx, prec).from_layers(layers, prior, 5, 5)
+    stages = pk.STAGE_ALL if cfg["nnet"] else (pk.STAGE_FBANK | pk.STAGE_CMVN)
+    batch = pk.Batch(ctx, [SAMPLES_10S] * n_utts, g, am, prob_scale=0.1)
+    batch.synth_pcm(1234, rank * n_utts)
+    ctx.sync()
+    frames = batch.total_frames
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        batch.run(stages)
+    ctx.sync()
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    barrier(dist, local)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ctx.timer_start()
+    for _ in range(args.steps):
+        batch.run(stages)
+    ms = ctx.timer_stop()
+    barrier(dist, local)
+    clocks = sampler.stop() if sampler else None
+    prof = ctx.profile_get()
+    ctx.profile_enable(False)
+    ms_max = max_over_ranks(dist, local, ms)
+    total_frames = sum_over_ranks(dist, local, float(frames))
+    value = total_frames * args.steps / (ms_max * 1e-3)
+    checksum = batch.checksum(pk.BUF_LOGLIK if cfg["nnet"] else pk.BUF_FEATS)
+
+    # ---- roofline of the dominant kernel, from the per-launch CUDA events of the timed region
+    gemm_launches, gemm_ms = prof["gemm"]
+    fb_ms = prof["fbank"][1] + prof["cmvn"][1]
+    front_gbs = 480.0 * frames * args.steps / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else None
+    if cfg["nnet"]:
+        achieved = flops_per_frame(cfg) * frames * args.steps / (gemm_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor_sustained"],
+                    "unit": "TFLOP/s", "frac": achieved / peaks["tensor_sustained"], "traffic": None,
+                    "kernel": "gemm_kernel (tcgen05, all %d layers)" % (cfg["hidden"] + 1),
+                    "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["src"],
+                    "avg_launch_ms": gemm_ms / max(gemm_launches, 1)}
+    else:
+        roofline = {"bound": "hbm", "achieved": front_gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": front_gbs / peaks["hbm"], "traffic": None,
+                    "kernel": "fbank_kernel + cmvn_kernel (480 algorithmic B/frame)",
+                    "peak_source": "%s hbm_gbs" % peaks["src"],
+                    "avg_launch_ms": fb_ms / max(prof["fbank"][0] + prof["cmvn"][0], 1)}
+    launches = int(sum(v[0] for v in prof.values()))
+
+    # ---- end to end through the host-buffer API: pinned PCM in, log-likelihoods out, per chunk
+    e2e = run_e2e(args, cfg, ctx, am, g, rank, local, dist, n_utts)
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference on this host's cores + parity sample
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_ref = reference_sample_size(cfg, cores)
+        try:
+            sec, f_ref, _ = time_reference(cfg, cores, n_ref, 1)
+            sec1, f1, _ = time_reference(cfg, 1, 1 if cfg["nnet"] else 8, 1)
+            cpu = {"value": f_ref / sec, "unit": "frames/s", "cores": cores, "kind": "reference",
+                   "sample": "%d synthetic 10 s utterances (%d frames), std::thread pool, oracle/_ref -O2"
+                             % (n_ref, f_ref),
+                   "single_thread_value": f1 / sec1}
+            parity = parity_sample(cfg, batch, layers, prior, g)
+        except Exception as e:  # the reference library is test infrastructure; report, don't die
+            cpu = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference",
+                   "sample": "unavailable: %s" % e}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if prec == pk.PREC_BF16 else "bf16x3", "data": "synthetic",
+            "config": {"workload": cfg["name"], "utts_per_gpu": n_utts, "frames_per_gpu": frames,
+                       "l2": "inputs larger than L2 (PCM %.2f GB, activations > 1 GB per layer)"
+                             % (batch.total_samples * 2 / 1e9),
+                       "parallelism": "utterance shards, no collective", "precision": args.precision},
+            "rtfx": value / 100.0,
+            "roofline": roofline,
+            "roofline_frontend": {"bound": "hbm (nominal; the fused fbank kernel is FP32/issue bound)",
+                                  "achieved": front_gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                                  "frac": (front_gbs / peaks["hbm"]) if front_gbs else None,
+                                  "fbank_ms_per_step": prof["fbank"][1] / args.steps,
+                                  "cmvn_ms_per_step": prof["cmvn"][1] / args.steps},
+            "kernel_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "checksum": checksum,
+            "parity": parity,
+            "device": ctx.device_name,
+        }
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if am:
+        am.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, cfg, ctx, am, g, rank, local, dist, n_utts):
+    """PCM in pinned host memory -> H2D -> hot path -> D2H of the result into pinned host
+    memory, chunk by chunk through the batch API, all inside the timed region."""
+    import pocketkaldi_b200 as pk
+    from pocketkaldi_b200.binding import PinnedArray
+    from pocketkaldi_b200.synth import synth_pcm
+    chunk = min(args.e2e_chunk, n_utts)
+    n_chunks = (n_utts + chunk - 1) // chunk
+    if n_utts % chunk:
+        n_chunks = n_utts // chunk  # whole chunks only; the metric is a rate
+    n_chunks = max(n_chunks, 1)
+    stages = pk.STAGE_ALL if cfg["nnet"] else (pk.STAGE_FBANK | pk.STAGE_CMVN)
+    which = pk.BUF_LOGLIK if cfg["nnet"] else pk.BUF_FEATS
+    cb = pk.Batch(ctx, [SAMPLES_10S] * chunk, g, am, prob_scale=0.1)
+    out_cols = cfg["pdfs"] if cfg["nnet"] else 40
+    pin_in = PinnedArray((chunk * SAMPLES_10S,), np.int16)
+    pin_out = PinnedArray((cb.total_frames, out_cols), np.float32)
+    pin_in.array[:] = synth_pcm(1234, np.arange(chunk) + rank * n_utts, SAMPLES_10S).reshape(-1)
+    h2d = pin_in.array.nbytes * n_chunks
+    d2h = pin_out.array.nbytes * n_chunks
+
+    def step():
+        for _ in range(n_chunks):
+            cb.set_pcm(pin_in.array)
+            cb.run(stages)
+            cb.get_rows_async(which, 0, cb.total_frames, pin_out.array)
+        ctx.sync()
+
+    for _ in range(min(args.warmup, 2)):
+        step()
+    barrier(dist, local)
+    steps = max(1, min(args.steps, args.e2e_steps))
+    ctx.timer_start()
+    for _ in range(steps):
+        step()
+    ms = ctx.timer_stop()
+    barrier(dist, local)
+    ms_max = max_over_ranks(dist, local, ms)
+    frames = sum_over_ranks(dist, local, float(cb.total_frames * n_chunks))
+    fin = bool(np.isfinite(pin_out.array[::997]).all())
+    cb.close()
+    pin_in.free()
+    pin_out.free()
+    return {"value": frames * steps / (ms_max * 1e-3), "unit": "frames/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
+            "ms_per_step": ms_max / steps, "chunk_utts": chunk, "chunks_per_step": n_chunks,
+            "finite": fin,
+            "api": "pkb_batch_set_pcm_i16 + pkb_batch_run + pkb_batch_get_rows (pinned host buffers)"}
+
+
+def parity_sample(cfg, batch, layers, prior, g):
+    """GPU output of utterance 0 against the unmodified reference on the same PCM (checker only)."""
+    import pocketkaldi_b200 as pk
+    from oracle.oracle import Reference
+    from pocketkaldi_b200.synth import synth_pcm
+    ref = Reference()
+    pcm = synth_pcm(1234, [0], SAMPLES_10S)[0].astype(np.float32)
+    raw = ref.fbank(pcm)
+    feats = ref.cmvn(raw, g)
+    out = {"frames": int(raw.shape[0])}
+    got_raw = np.empty((FRAMES_10S, 40), np.float32)
+    batch.get_rows_async(pk.BUF_RAW, 0, FRAMES_10S, got_raw)
+    got_ft = np.empty((FRAMES_10S, 40), np.float32)
+    batch.get_rows_async(pk.BUF_FEATS, 0, FRAMES_10S, got_ft)
+    batch.ctx.sync()
+    out["fbank_max_rel_err"] = float(np.max(np.abs(got_raw - raw) / np.abs(raw)))
+    out["cmvn_max_err_rel_to_max1"] = float(np.max(np.abs(got_ft - feats) / np.maximum(1.0, np.abs(feats))))
+    if cfg["nnet"]:
+        with tempfile.TemporaryDirectory(prefix="pkb_parity_") as tmp:
+            conf, _, _ = write_reference_model(cfg, tmp)
+            am = ref.am_load(conf)
+            ll_ref = ref.am_compute(am, feats) * np.float32(0.1)
+            ref.am_free(am)
+        got = np.empty((FRAMES_10S, cfg["pdfs"]), np.float32)
+        batch.get_rows_async(pk.BUF_LOGLIK, 0, FRAMES_10S, got)
+        batch.ctx.sync()
+        out["loglik_max_abs_err_unscaled"] = float(np.max(np.abs(got - ll_ref)) / 0.1)
+        out["argmax_agreement"] = float(np.mean(got.argmax(1) == ll_ref.argmax(1)))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="3", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--utts", type=int, default=0, help="utterances per GPU (default: the config's)")
+    ap.add_argument("--e2e-chunk", type=int, default=256)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+    else:
+        run_gpu_arm(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

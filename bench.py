@@ -293,7 +293,7 @@ def run_gpu_arm(args, cfg):
     launches = int(sum(v[0] for v in prof.values()))
 
     # ---- end to end through the host-buffer API: pinned PCM in, log-likelihoods out, per chunk
-    e2e = run_e2e(args, cfg, ctx, am, g, rank, local, dist, n_utts)
+    e2e = None if args.no_e2e else run_e2e(args, cfg, ctx, am, g, rank, local, dist, n_utts)
 
     # ---- CPU baseline (rank 0, N=1 only): the reference on this host's cores + parity sample
     cpu = None
@@ -441,6 +441,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

@@ -1,0 +1,86 @@
+"""Word-output parity through the reference's UNCHANGED CPU Viterbi decoder: the reference's
+main.cc / pocketkaldi.cc / decoder.cc compiled against pocketkaldi_b200/shim (so that
+Fbank / CMVN / AcousticModel / pk_decodable_* run on the GPU through the C ABI) must print
+the same hypotheses as the pure reference CLI on the repo's two test wavs."""
+
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from pocketkaldi_b200 import formats
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM_CLI = os.path.join(ROOT, "oracle", "_ref", "pocketkaldi_b200_cli")
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "pocketkaldi_ref")
+
+
+def run_cli(cli, conf, inp, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    out = subprocess.run([cli, conf, inp], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         timeout=120, env=e, check=True).stdout.decode()
+    res = []
+    for line in out.strip().splitlines():
+        path, hyp, llpf = line.split("\t")
+        res.append((os.path.basename(path), hyp.strip(), float(llpf)))
+    return res
+
+
+@pytest.fixture(scope="module")
+def wavs(tmp_path_factory, golden):
+    d = tmp_path_factory.mktemp("wavs")
+    paths = {}
+    for name in ("hello", "cat"):
+        p = str(d / ("en-us-%s.wav" % name))
+        formats.write_wav16(p, golden[name + "_pcm"])
+        paths[name] = p
+    scp = str(d / "all.scp")
+    with open(scp, "w") as fd:
+        fd.write(paths["hello"] + "\n" + paths["cat"] + "\n")
+    paths["scp"] = scp
+    return paths
+
+
+def golden_hyps():
+    out = {}
+    for line in open(os.path.join(ROOT, "tests", "golden", "toy_decode_ref.txt")):
+        name, hyp, llpf = line.rstrip("\n").split("\t")
+        out[name] = (hyp.strip(), float(llpf))
+    return out
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_words_identical_to_reference(wavs, toy_conf, precision):
+    if not os.path.exists(SHIM_CLI):
+        pytest.skip("oracle/_ref/pocketkaldi_b200_cli not built (needs /root/reference at build time)")
+    gold = golden_hyps()
+    for name in ("hello", "cat"):
+        (_, hyp, llpf), = run_cli(SHIM_CLI, toy_conf, wavs[name], {"PKB_PRECISION": precision})
+        assert hyp == gold[name][0], (name, hyp, gold[name][0])
+        tol = 2e-3 if precision == "bf16x3" else 2e-2
+        assert abs(llpf - gold[name][1]) < tol
+    # .scp input (src/main.cc:34-46)
+    res = run_cli(SHIM_CLI, toy_conf, wavs["scp"], {"PKB_PRECISION": precision})
+    assert [r[1] for r in res] == [gold["hello"][0], gold["cat"][0]]
+
+
+def test_live_reference_cli_agrees(wavs, toy_conf):
+    if not (os.path.exists(SHIM_CLI) and os.path.exists(REF_CLI)):
+        pytest.skip("oracle/_ref CLIs not built")
+    a = run_cli(SHIM_CLI, toy_conf, wavs["scp"])
+    b = run_cli(REF_CLI, toy_conf, wavs["scp"])
+    assert [x[1] for x in a] == [x[1] for x in b]
+    for x, y in zip(a, b):
+        assert abs(x[2] - y[2]) < 2e-3
+
+
+def test_shim_reports_reference_style_load_errors(tmp_path):
+    if not os.path.exists(SHIM_CLI):
+        pytest.skip("shim CLI not built")
+    bad = str(tmp_path / "missing.conf")
+    r = subprocess.run([SHIM_CLI, bad, "x.wav"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert r.returncode == 1 and b"pocketkaldi:" in r.stdout

@@ -274,7 +274,8 @@ def run_gpu_arm(args, cfg):
     checksum = batch.checksum(pk.BUF_LOGLIK if cfg["nnet"] else pk.BUF_FEATS)
 
     # ---- roofline of the dominant kernel, from the per-launch CUDA events of the timed region
-    gemm_launches, gemm_ms = prof["gemm"]
+    gemm_launches = prof["gemm"][0] + prof["gemm_final"][0]
+    gemm_ms = prof["gemm"][1] + prof["gemm_final"][1]
     fb_ms = prof["fbank"][1] + prof["cmvn"][1]
     front_gbs = 480.0 * frames * args.steps / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else None
     if cfg["nnet"]:

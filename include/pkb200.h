@@ -197,8 +197,8 @@ int pkb_timer_stop(pkb_ctx_t *ctx, float *elapsed_ms); /* synchronises */
  * accumulated per kernel class. */
 #define PKB_KERNEL_FBANK 0
 #define PKB_KERNEL_CMVN 1
-#define PKB_KERNEL_GEMM 2
-#define PKB_KERNEL_FINALIZE 3
+#define PKB_KERNEL_GEMM 2       /* hidden-layer GEMMs (fused bias/ReLU/normalize epilogue)    */
+#define PKB_KERNEL_GEMM_FINAL 3 /* output-layer GEMM (fused log-softmax / prior / scale)      */
 #define PKB_KERNEL_MISC 4
 #define PKB_KERNEL_CLASSES 5
 int pkb_profile_enable(pkb_ctx_t *ctx, int on);

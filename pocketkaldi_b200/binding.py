@@ -21,7 +21,7 @@ CSRC = os.path.join(HERE, "csrc")
 PREC_BF16, PREC_BF16X3 = 0, 1
 STAGE_FBANK, STAGE_CMVN, STAGE_NNET, STAGE_ALL = 1, 2, 4, 7
 BUF_PCM, BUF_RAW, BUF_FEATS, BUF_LOGLIK = 0, 1, 2, 3
-KERNEL_CLASSES = ("fbank", "cmvn", "gemm", "finalize", "misc")
+KERNEL_CLASSES = ("fbank", "cmvn", "gemm", "gemm_final", "misc")
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")

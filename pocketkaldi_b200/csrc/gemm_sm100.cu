@@ -19,7 +19,10 @@
 // each K step issues hi*hi + lo*hi + hi*lo into the same accumulator, which brings
 // the product error down to ~2^-16 relative (FP32-class for this workload).
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <vector>
 
 #include "gemm_sm100.cuh"
 
@@ -27,7 +30,9 @@ namespace pkb {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kMainThreads = 128;   // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare
+constexpr int epi_warps(bool final) { return final ? 8 : 4; }
+constexpr int num_threads(bool final) { return kMainThreads + 32 * epi_warps(final); }
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemBudget = 227 * 1024;
 
@@ -66,10 +71,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 
 // Bounded wait: a pipeline bug turns into a trap (reported as a launch failure)
 // instead of hanging the GPU.
+template <int kSleepNs = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (kSleepNs > 0) __nanosleep(kSleepNs);  // keep the spinning lane off the issue port
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
@@ -168,36 +175,89 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(int *p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ float exp2f_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
 struct SmemLayout {
-  uint32_t stage_bytes, a_plane, w_plane, stages, bar_off, total;
+  uint32_t stage_bytes, a_plane, w_plane, stages, epi_off, epi_bytes, bar_off, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int planes) {
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool final) {
   SmemLayout L;
   L.a_plane = kBlockM * kBlockK * 2;
   L.w_plane = block_n * kBlockK * 2;
   L.stage_bytes = planes * (L.a_plane + L.w_plane);
-  uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */;
+  // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
+  // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch
+  L.epi_bytes = final ? 8 * 4096 + 2 * block_n * 4 + 128 * 8 : 4 * planes * 4096;
+  uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */ - L.epi_bytes;
   L.stages = avail / L.stage_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
-  L.bar_off = L.stages * L.stage_bytes;
+  L.epi_off = L.stages * L.stage_bytes;
+  L.bar_off = L.epi_off + L.epi_bytes;
   L.total = L.bar_off + 256 + 1024;
   return L;
 }
 
 // ---------------------------------------------------------------- kernel
+// Persistent tile schedule. Default: tiles dealt round-robin with N fastest. Grouped (final
+// softmax stage): the grid is a whole number of groups of n_tiles_n CTAs; a group owns one
+// row block per iteration and each of its CTAs always owns the same column tile, so the CTAs
+// that exchange softmax partials are a fixed team working on the same iteration.
+__device__ __forceinline__ bool get_tile(const GemmParams &p, int it, int &m_blk, int &n_blk) {
+  if (p.group_sched) {
+    const int groups = gridDim.x / p.n_tiles_n;
+    m_blk = static_cast<int>(blockIdx.x) / p.n_tiles_n + it * groups;
+    n_blk = static_cast<int>(blockIdx.x) % p.n_tiles_n;
+    return m_blk < p.m_tiles;
+  }
+  const int tile = blockIdx.x + it * gridDim.x;
+  if (tile >= p.num_tiles) return false;
+  m_blk = tile / p.n_tiles_n;
+  n_blk = tile % p.n_tiles_n;
+  return true;
+}
+
 template <int BN, int PLANES, bool FINAL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(num_threads(FINAL), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
             const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const SmemLayout L = smem_layout(BN, PLANES);
+  const SmemLayout L = smem_layout(BN, PLANES, FINAL);
   uint8_t *smem = reinterpret_cast<uint8_t *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
@@ -225,7 +285,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], epi_warps(FINAL));
     }
     fence_barrier_init();
   }
@@ -242,11 +302,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles_n) * kBlockM;
-        const int n0 = (tile % p.n_tiles_n) * BN;
+      int m_blk, n_blk;
+      for (int it = 0; get_tile(p, it, m_blk, n_blk); ++it) {
+        const int m0 = m_blk * kBlockM;
+        const int n0 = n_blk * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait<64>(&empty[s], ph ^ 1);
           uint8_t *st = smem + s * L.stage_bytes;
           mbar_expect_tx(&full[s], L.stage_bytes);
           tma_load_2d(st, &tm_a_hi, &full[s], kb * kBlockK, m0);
@@ -264,10 +325,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kBlockM, BN);
       uint32_t s = 0, ph = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      int m_blk, n_blk;
+      for (int it = 0; get_tile(p, it, m_blk, n_blk); ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(&tempty[as], aph ^ 1);
+        mbar_wait<32>(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -301,13 +362,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quadrant
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    // FINAL runs 8 epilogue warps: two per lane quadrant, each owning half of the columns
+    const int chalf = FINAL ? ((warp - 4) >> 2) : 0;
+    // per-warp staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7);
+    // rows are written by their owner lane and read back 4 rows per instruction so that
+    // every global store covers whole 128-byte lines
+    uint8_t *stg = smem + L.epi_off + (FINAL ? (warp - 4) * 4096 : q * (PLANES * 4096));
+    const uint32_t stg_w = smem_u32(stg) + lane * 128;          // this lane's row
+    // grouped schedule: this CTA's column tile never changes, keep its bias / log-prior in smem
+    float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + 8 * 4096);
+    float *s_lp = s_bias + BN;
+    constexpr int kEpiThreads = 32 * epi_warps(FINAL);
+    if (FINAL && p.group_sched) {
+      const int nb = static_cast<int>(blockIdx.x) % p.n_tiles_n;
+      for (int i = threadIdx.x - kMainThreads; i < BN; i += kEpiThreads) {
+        s_bias[i] = p.bias[nb * BN + i];
+        s_lp[i] = p.log_prior[nb * BN + i];
+      }
+      named_bar_sync(1, kEpiThreads);
+    }
+    const int t_row = lane >> 3, t_chunk = lane & 7;            // transposed read role
+    int m_blk, n_blk;
+    for (int it = 0; get_tile(p, it, m_blk, n_blk); ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
-      const int n_blk = tile % p.n_tiles_n;
-      const int m0 = (tile / p.n_tiles_n) * kBlockM;
+      const int m0 = m_blk * kBlockM;
       const int n0 = n_blk * BN;
-      const int row = m0 + q * 32 + lane;
+      const int wrow0 = m0 + q * 32;  // first row of this warp
+      const int row = wrow0 + lane;
       const bool row_ok = row < p.M;
 
       float rs = 1.0f;
@@ -318,100 +399,251 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         rs = sqrtf(p.in_dim / ss);  // NormalizeLayer: no floor (src/nnet.cc:71-73)
       }
 
-      mbar_wait(&tfull[as], aph);
+      long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0;
+      const bool dbg_on = FINAL && p.dbg != nullptr && warp == 4 && lane == 0;
+      if (dbg_on) tk0 = clock64();
+      mbar_wait<32>(&tfull[as], aph);
       tc_fence_after();
+      if (dbg_on) tk1 = clock64();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 
-      float sumsq = 0.0f;
-      float run_max = -INFINITY, run_sum = 0.0f;
-      int dest = -1;
-      if (FINAL && row_ok) dest = p.row_map ? p.row_map[row] : row;
-
+      if (!FINAL) {
+        float sumsq = 0.0f;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        float z[32];
+        for (int g = 0; g < BN / 64; ++g) {
+          const int col0 = n0 + g * 64;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + i));
-          z[i + 0] = fmaf(__uint_as_float(v[i + 0]), rs, b.x);
-          z[i + 1] = fmaf(__uint_as_float(v[i + 1]), rs, b.y);
-          z[i + 2] = fmaf(__uint_as_float(v[i + 2]), rs, b.z);
-          z[i + 3] = fmaf(__uint_as_float(v[i + 3]), rs, b.w);
-        }
-        if (!FINAL) {
-          if (p.relu) {
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(taddr + g * 64 + h * 32, v);
+            tmem_ld_wait();
+            float z[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) z[i] = fmaxf(z[i], 0.0f);
-          }
-          if (p.out_sumsq != nullptr) {
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + h * 32 + i));
+              z[i + 0] = fmaf(__uint_as_float(v[i + 0]), rs, b.x);
+              z[i + 1] = fmaf(__uint_as_float(v[i + 1]), rs, b.y);
+              z[i + 2] = fmaf(__uint_as_float(v[i + 2]), rs, b.z);
+              z[i + 3] = fmaf(__uint_as_float(v[i + 3]), rs, b.w);
+            }
+            if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sumsq = fmaf(z[i], z[i], sumsq);
-          }
-          if (row_ok) {
+              for (int i = 0; i < 32; ++i) z[i] = fmaxf(z[i], 0.0f);
+            }
+            if (p.out_sumsq != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sumsq = fmaf(z[i], z[i], sumsq);
+            }
             uint32_t hi[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) hi[i] = pack_bf16(z[2 * i], z[2 * i + 1]);
-            uint4 *dst = reinterpret_cast<uint4 *>(p.out_hi + static_cast<size_t>(row) * p.ld_out + col0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            for (int j = 0; j < 4; ++j)
+              st_shared_v4(stg_w + (((h * 4 + j) ^ (lane & 7)) << 4), hi[4 * j], hi[4 * j + 1],
+                           hi[4 * j + 2], hi[4 * j + 3]);
             if (PLANES == 2) {
               uint32_t lo[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162 *>(&hi[i]);
-                lo[i] = pack_bf16(z[2 * i] - __low2float(h), z[2 * i + 1] - __high2float(h));
+                const __nv_bfloat162 hh = *reinterpret_cast<__nv_bfloat162 *>(&hi[i]);
+                lo[i] = pack_bf16(z[2 * i] - __low2float(hh), z[2 * i + 1] - __high2float(hh));
               }
-              uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + static_cast<size_t>(row) * p.ld_out + col0);
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              for (int j = 0; j < 4; ++j)
+                st_shared_v4(stg_w + 4096 + (((h * 4 + j) ^ (lane & 7)) << 4), lo[4 * j],
+                             lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
           }
-        } else {
-          const int nvalid = p.N_valid - col0;  // columns of this chunk that are real
-          if (p.lse_part != nullptr && nvalid > 0) {
-            float cmax = -INFINITY;
+          __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nvalid) cmax = fmaxf(cmax, z[i]);
-            const float nm = fmaxf(run_max, cmax);
-            float acc = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nvalid) acc += __expf(z[i] - nm);
-            run_sum = run_sum * __expf(run_max - nm) + acc;
-            run_max = nm;
-          }
-          if (dest >= 0 && nvalid > 0) {
-            float *dst = p.out_f32 + static_cast<size_t>(dest) * p.ld_f32 + col0;
-            if (nvalid >= 32 && (p.ld_f32 & 3) == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4 *>(dst + i) = make_float4(z[i], z[i + 1], z[i + 2], z[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < nvalid) dst[i] = z[i];
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + t_row;
+            if (wrow0 + rr < p.M) {
+              const uint32_t src = smem_u32(stg) + rr * 128 + ((t_chunk ^ (rr & 7)) << 4);
+              const size_t off = static_cast<size_t>(wrow0 + rr) * p.ld_out + col0 + t_chunk * 8;
+              *reinterpret_cast<uint4 *>(p.out_hi + off) = ld_shared_v4(src);
+              if (PLANES == 2) *reinterpret_cast<uint4 *>(p.out_lo + off) = ld_shared_v4(src + 4096);
             }
           }
+          __syncwarp();
         }
-      }
-      // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-
-      if (!FINAL) {
+        // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
         if (p.out_sumsq != nullptr && row_ok)
           p.out_sumsq[static_cast<size_t>(row) * p.n_tiles_n + n_blk] = sumsq;
       } else {
-        if (p.lse_part != nullptr && row_ok)
-          p.lse_part[static_cast<size_t>(row) * p.n_tiles_n + n_blk] = make_float2(run_max, run_sum);
+        // ---- pass 1 (softmax only): per-row (max, sum exp) over this warp's half of the
+        //      tile's columns, exchanged with the warps / CTAs that own the other columns
+        constexpr int kChunks = BN / 64;  // 32-column chunks per epilogue warp
+        const int cbase = chalf * (BN / 2);
+        const float kLog2e = 1.4426950408889634f;
+        float lse = 0.0f;
+        if (p.final_mode != 0) {
+          float run_max = -INFINITY, run_sum = 0.0f;
+#pragma unroll 1
+          for (int c = 0; c < kChunks; ++c) {
+            const int col0 = n0 + cbase + c * 32;
+            const int nvalid = p.N_valid - col0;
+            if (nvalid <= 0) break;
+            uint32_t v[32];
+            tmem_ld32(taddr + cbase + c * 32, v);
+            tmem_ld_wait();
+            float z[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = *reinterpret_cast<const float4 *>(s_bias + cbase + c * 32 + i);
+              z[i + 0] = fmaf(__uint_as_float(v[i + 0]), rs, b.x);
+              z[i + 1] = fmaf(__uint_as_float(v[i + 1]), rs, b.y);
+              z[i + 2] = fmaf(__uint_as_float(v[i + 2]), rs, b.z);
+              z[i + 3] = fmaf(__uint_as_float(v[i + 3]), rs, b.w);
+            }
+            if (nvalid < 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i >= nvalid) z[i] = -INFINITY;  // padding columns: exp() == 0
+            }
+            float cmax = z[0];
+#pragma unroll
+            for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, z[i]);
+            const float nm = fmaxf(run_max, cmax);
+            const float off = -nm * kLog2e;
+            float acc = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc += exp2f_fast(fmaf(z[i], kLog2e, off));
+            run_sum = run_sum * exp2f_fast((run_max - nm) * kLog2e) + acc;
+            run_max = nm;
+          }
+          // (1) fold the two column halves of this CTA in shared memory
+          float2 *s_half = reinterpret_cast<float2 *>(s_lp + BN);  // [128]
+          const int rit = q * 32 + lane;  // row inside the tile
+          if (chalf == 1) s_half[rit] = make_float2(run_max, run_sum);
+          if (dbg_on) tk2 = clock64();
+          named_bar_sync(1, kEpiThreads);
+          // (2) publish one (max, sum) per row and column tile, row-fastest so that every
+          //     warp-wide access to the exchange buffer is one contiguous 256-byte segment
+          float2 *xbase = p.lse_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
+          if (chalf == 0) {
+            const float2 o = s_half[rit];
+            const float nm = fmaxf(run_max, o.x);
+            const float sm = run_sum * exp2f_fast((run_max - nm) * kLog2e) +
+                             o.y * exp2f_fast((o.x - nm) * kLog2e);
+            __stcg(&xbase[n_blk * kBlockM + rit], make_float2(nm, sm));
+          }
+          named_bar_sync(1, kEpiThreads);
+          // (3) one thread makes the CTA's partials visible device-wide, signals, and waits for
+          //     the peer CTAs of this row block (relaxed polling, a single acquire at the end)
+          if (warp == 4 && lane == 0) {
+            __threadfence();
+            red_release_add(p.tile_done + m_blk, 1);
+            const long long t0 = clock64();
+            while (ld_relaxed(p.tile_done + m_blk) < p.n_tiles_n) {
+              if (clock64() - t0 > 4000000000ll) __trap();
+            }
+            __threadfence();
+          }
+          named_bar_sync(1, kEpiThreads);
+          if (dbg_on) tk3 = clock64();
+          // (4) combine the n_tiles_n partials of this row (coalesced, independent loads)
+          {
+            float mx = -INFINITY, ssum = 0.0f;
+            for (int j = 0; j < p.n_tiles_n; ++j) {
+              const float2 e = __ldcg(&xbase[j * kBlockM + rit]);
+              const float nm = fmaxf(mx, e.x);
+              ssum = ssum * exp2f_fast((mx - nm) * kLog2e) + e.y * exp2f_fast((e.x - nm) * kLog2e);
+              mx = nm;
+            }
+            lse = mx + logf(ssum);
+          }
+        }
+        if (dbg_on) tk4 = clock64();
+        // ---- pass 2: final values, staged and written as whole 128-byte lines
+        int dest = -1;
+        if (row_ok) dest = p.row_map ? p.row_map[row] : row;
+        const bool vec_ok = (p.ld_f32 & 3) == 0;
+        const float floor_v = p.log_floor, sc = p.scale;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+          const int col0 = n0 + cbase + c * 32;
+          const int nvalid = p.N_valid - col0;
+          if (nvalid <= 0) break;
+          uint32_t v[32];
+          long long u0 = 0, u1 = 0, u2 = 0;
+          if (dbg_on) u0 = clock64();
+          tmem_ld32(taddr + cbase + c * 32, v);
+          tmem_ld_wait();
+          if (dbg_on) u1 = clock64();
+          float z[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = p.group_sched
+                                 ? *reinterpret_cast<const float4 *>(s_bias + cbase + c * 32 + i)
+                                 : __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + i));
+            z[i + 0] = fmaf(__uint_as_float(v[i + 0]), rs, b.x);
+            z[i + 1] = fmaf(__uint_as_float(v[i + 1]), rs, b.y);
+            z[i + 2] = fmaf(__uint_as_float(v[i + 2]), rs, b.z);
+            z[i + 3] = fmaf(__uint_as_float(v[i + 3]), rs, b.w);
+          }
+          if (p.final_mode == 1) {  // softmax probabilities (Nnet::Propagate)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) z[i] = expf(z[i] - lse);
+          } else if (p.final_mode == 2) {  // scaled log-likelihood (src/am.cc:106-112, decodable.cc:15)
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              // log_prior is padded to N_pad, so the vector load is always in bounds
+              const float4 lp = *reinterpret_cast<const float4 *>(s_lp + cbase + c * 32 + i);
+              z[i + 0] = (fmaxf(z[i + 0] - lse, floor_v) - lp.x) * sc;
+              z[i + 1] = (fmaxf(z[i + 1] - lse, floor_v) - lp.y) * sc;
+              z[i + 2] = (fmaxf(z[i + 2] - lse, floor_v) - lp.z) * sc;
+              z[i + 3] = (fmaxf(z[i + 3] - lse, floor_v) - lp.w) * sc;
+            }
+          }
+          if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(stg_w + ((j ^ (lane & 7)) << 4), __float_as_uint(z[4 * j]),
+                           __float_as_uint(z[4 * j + 1]), __float_as_uint(z[4 * j + 2]),
+                           __float_as_uint(z[4 * j + 3]));
+            __syncwarp();
+            if (dbg_on) u2 = clock64();
+            const bool col_ok = t_chunk * 4 < nvalid;
+            float *gbase = p.out_f32 + col0 + t_chunk * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + t_row;
+              const int d = __shfl_sync(0xffffffffu, dest, rr);
+              if (d >= 0 && col_ok) {
+                const uint32_t src = smem_u32(stg) + rr * 128 + ((t_chunk ^ (rr & 7)) << 4);
+                *reinterpret_cast<uint4 *>(gbase + static_cast<size_t>(d) * p.ld_f32) = ld_shared_v4(src);
+              }
+            }
+            __syncwarp();
+            if (dbg_on) {
+              const long long u3 = clock64();
+              p.dbg[static_cast<size_t>(blockIdx.x) * 8 + 6] += u1 - u0;
+              p.dbg[static_cast<size_t>(blockIdx.x) * 8 + 7] += u3 - u2;
+            }
+          } else if (dest >= 0) {
+            float *dst = p.out_f32 + static_cast<size_t>(dest) * p.ld_f32 + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) dst[i] = z[i];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        if (dbg_on) {
+          const long long tk5 = clock64();
+          long long *d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
+          d[0] += tk1 - tk0;  // wait for the accumulator
+          d[1] += tk2 - tk1;  // pass 1
+          d[2] += tk3 - tk2;  // publish + peer wait
+          d[3] += tk4 - tk3;  // combine partials
+          d[4] += tk5 - tk4;  // pass 2
+          d[5] += 1;
+        }
       }
     }
   }
@@ -444,19 +676,61 @@ EncodeTiledFn get_encode_fn() {
 template <int BN, int PLANES, bool FINAL>
 int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const CUtensorMap *w_hi,
                const CUtensorMap *w_lo, const GemmParams &p) {
-  const SmemLayout L = smem_layout(BN, PLANES);
+  const SmemLayout L = smem_layout(BN, PLANES, FINAL);
   auto kern = gemm_kernel<BN, PLANES, FINAL>;
   PKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  const int grid = std::min(p.num_tiles, c->sm_count);
-  LaunchScope scope(c, PKB_KERNEL_GEMM);
-  kern<<<grid, kThreads, L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, p);
+  int grid = std::min(p.num_tiles, c->sm_count);
+  GemmParams pp = p;
+  pp.m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  pp.group_sched = 0;
+  if (FINAL && p.final_mode != 0) {
+    if (p.n_tiles_n > c->sm_count) {
+      set_error("launch_gemm: %d column tiles exceed the %d SMs of the device", p.n_tiles_n, c->sm_count);
+      return PKB_ERR_UNSUPPORTED;
+    }
+    pp.group_sched = 1;
+    grid = std::min(c->sm_count / p.n_tiles_n, pp.m_tiles) * p.n_tiles_n;
+  }
+  static const bool dbg_env = getenv("PKB_GEMM_DEBUG") != nullptr;
+  long long *dbg = nullptr;
+  if (dbg_env && FINAL && p.final_mode != 0) {
+    cudaMalloc(&dbg, sizeof(long long) * 8 * grid);
+    cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * grid, c->stream);
+  }
+  pp.dbg = dbg;
+  {
+  LaunchScope scope(c, FINAL ? PKB_KERNEL_GEMM_FINAL : PKB_KERNEL_GEMM);
+  if (FINAL && p.final_mode != 0) {
+    // the column tiles of a row block exchange softmax partials through global memory and wait
+    // for each other: a cooperative launch guarantees that all CTAs are co-resident
+    PKB_CUDA(cudaMemsetAsync(p.tile_done, 0, sizeof(int) * ((p.M + kBlockM - 1) / kBlockM), c->stream));
+    CUtensorMap m0 = *a_hi, m1 = *a_lo, m2 = *w_hi, m3 = *w_lo;
+    void *args[] = {&m0, &m1, &m2, &m3, &pp};
+    PKB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid),
+                                         dim3(num_threads(FINAL)), args, L.total, c->stream));
+  } else {
+    kern<<<grid, num_threads(FINAL), L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, pp);
+  }
   PKB_CUDA(cudaGetLastError());
+  }
+  if (dbg) {
+    std::vector<long long> h(8 * grid);
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(h.data(), dbg, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+    cudaFree(dbg);
+    double s[8] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 8; ++k) s[k] += h[8 * b + k];
+    const double n = s[5] > 0 ? s[5] : 1;
+    fprintf(stderr, "[pkb gemm final] tiles/cta=%.0f cycles/tile: wait_acc=%.0f pass1=%.0f sync=%.0f combine=%.0f pass2=%.0f (tmem_ld=%.0f store=%.0f)\n",
+            n / grid, s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n, s[6] / n, s[7] / n);
+  }
   return PKB_OK;
 }
 
 }  // namespace
 
-int gemm_max_smem_bytes(int block_n, int planes) { return smem_layout(block_n, planes).total; }
+int gemm_max_smem_bytes(int block_n, int planes) { return smem_layout(block_n, planes, true).total; }
 
 int make_tensor_map(CUtensorMap *map, const void *base, uint64_t cols, uint64_t rows,
                     uint64_t pitch_bytes, uint32_t box_rows) {

@@ -23,12 +23,17 @@ constexpr int kUmmaK = 16;     // K of one tcgen05.mma kind::f16
 //                                                          preceding NormalizeLayer, else 1
 //   hidden   : y = relu ? max(z, 0) : z ; optional per-row sum of y^2 (for a following
 //              NormalizeLayer); stored as BF16 hi (+ lo = bf16(y - hi) in BF16X3)
-//   final    : z stored as FP32 at row_map[row] (skipped when < 0) plus per-(row, n-tile)
-//              online-softmax partials (max, sum exp(z - max))
+//   final    : FP32 output at row_map[row] (skipped when < 0). With a SoftmaxLayer the CTAs that
+//              own the column tiles of one row block exchange per-row (max, sum exp) partials
+//              through global memory while the accumulators stay in TMEM, then write
+//              softmax(z) or prob_scale * (max(log softmax(z), log 1e-20) - log_prior) once --
+//              no second pass over the [frames x pdfs] matrix.
 struct GemmParams {
   int M;               // rows of A / D
   int n_tiles_n;       // N_pad / block_n
   int num_tiles;       // m_tiles * n_tiles_n
+  int m_tiles;         // set by the launcher
+  int group_sched;     // set by the launcher: grouped schedule of the final softmax stage
   int num_kb;          // K_pad / kBlockK
   int N_valid;         // logical N (columns >= N_valid are padding)
   const float *bias;   // [N_pad], zero in the padding
@@ -42,7 +47,13 @@ struct GemmParams {
   float *out_f32;      // final: [rows][ld_f32]
   int ld_f32;
   const int32_t *row_map;  // final: [M] destination row or -1; nullptr = identity
-  float2 *lse_part;    // final: [M][n_tiles_n], nullptr when no softmax follows
+  // final_mode: 0 raw logits, 1 softmax probabilities, 2 scale*(max(log softmax, log_floor) - log_prior)
+  int final_mode;
+  float2 *lse_part;    // final softmax: [M][n_tiles_n] (max, sum exp) exchanged between column tiles
+  int *tile_done;      // final softmax: [m_tiles] arrival counters (zeroed by the launcher)
+  const float *log_prior;  // [N_pad]
+  float scale, log_floor;
+  long long *dbg;      // optional phase-cycle counters [grid][8] (PKB_GEMM_DEBUG=1), else nullptr
 };
 
 // Encodes a 2-D BF16 K-major tensor map: inner dim `cols` (K), outer dim `rows`,

@@ -84,58 +84,6 @@ __global__ void pack_plain_kernel(const float *__restrict__ in, int64_t rows, in
   if (lo) lo[g] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-// Second half of SoftmaxLayer + AM epilogue + decodable scale. One block per GEMM row.
-//   lse  = log sum_j exp(z_j) from the per-tile (max, sum) partials
-//   prob : exp(z - lse)
-//   ll   : scale * (max(z - lse, log(1e-20f)) - log_prior)     (src/am.cc:106-112,
-//          src/decodable.cc:15; log(max(p, floor)) == max(log p, log floor))
-__global__ void __launch_bounds__(256)
-finalize_kernel(float *__restrict__ out, int ld, int n_valid, const float2 *__restrict__ lse_part,
-                int n_tiles, const int32_t *__restrict__ row_map, int64_t rows, int mode,
-                float scale, float log_floor, const float *__restrict__ log_prior) {
-  for (int64_t m = blockIdx.x; m < rows; m += gridDim.x) {
-    const int64_t dest = row_map ? row_map[m] : m;
-    if (dest < 0) continue;
-    float mx = -INFINITY;
-    for (int i = 0; i < n_tiles; ++i) mx = fmaxf(mx, lse_part[m * n_tiles + i].x);
-    float s = 0.0f;
-    for (int i = 0; i < n_tiles; ++i) {
-      const float2 p = lse_part[m * n_tiles + i];
-      s += p.y * expf(p.x - mx);
-    }
-    const float lse = mx + logf(s);
-    float *row = out + dest * ld;
-    if ((ld & 3) == 0) {
-      float4 *row4 = reinterpret_cast<float4 *>(row);
-      const float4 *lp4 = reinterpret_cast<const float4 *>(log_prior);
-      for (int j = threadIdx.x; j < (n_valid >> 2); j += blockDim.x) {
-        float4 z = row4[j];
-        if (mode == kFinalProb) {
-          z.x = expf(z.x - lse); z.y = expf(z.y - lse); z.z = expf(z.z - lse); z.w = expf(z.w - lse);
-        } else {
-          const float4 lp = lp4[j];
-          z.x = (fmaxf(z.x - lse, log_floor) - lp.x) * scale;
-          z.y = (fmaxf(z.y - lse, log_floor) - lp.y) * scale;
-          z.z = (fmaxf(z.z - lse, log_floor) - lp.z) * scale;
-          z.w = (fmaxf(z.w - lse, log_floor) - lp.w) * scale;
-        }
-        row4[j] = z;
-      }
-      for (int j = (n_valid & ~3) + threadIdx.x; j < n_valid; j += blockDim.x) {
-        const float z = row[j];
-        row[j] = mode == kFinalProb ? expf(z - lse)
-                                    : (fmaxf(z - lse, log_floor) - log_prior[j]) * scale;
-      }
-    } else {
-      for (int j = threadIdx.x; j < n_valid; j += blockDim.x) {
-        const float z = row[j];
-        row[j] = mode == kFinalProb ? expf(z - lse)
-                                    : (fmaxf(z - lse, log_floor) - log_prior[j]) * scale;
-      }
-    }
-  }
-}
-
 __global__ void scale_kernel(float *x, int64_t n, float s) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -200,6 +148,7 @@ void Workspace::release() {
     sumsq[i].release();
   }
   lse_part.release();
+  tile_done.release();
   row_map.release();
   feat_hi.release();
   feat_lo.release();
@@ -291,12 +240,14 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
   }
   if (rc == PKB_OK) {
     // log prior: log in double, stored float (src/am.cc:42-43, src/vector.cc:333-339)
-    std::vector<float> lp(am->num_pdfs, 0.0f);
+    // padded to the last stage's n_pad so that the epilogue can use vector loads
+    const int lp_len = std::max(am->num_pdfs, am->stages.back().n_pad);
+    std::vector<float> lp(lp_len, 0.0f);
     if (prior)
       for (int j = 0; j < am->num_pdfs; ++j) lp[j] = static_cast<float>(log(static_cast<double>(prior[j])));
-    rc = am->log_prior.ensure(sizeof(float) * am->num_pdfs);
+    rc = am->log_prior.ensure(sizeof(float) * lp_len);
     if (rc == PKB_OK &&
-        cudaMemcpy(am->log_prior.p, lp.data(), sizeof(float) * am->num_pdfs,
+        cudaMemcpy(am->log_prior.p, lp.data(), sizeof(float) * lp_len,
                    cudaMemcpyHostToDevice) != cudaSuccess) {
       set_error("log prior upload failed");
       rc = PKB_ERR_CUDA;
@@ -343,7 +294,9 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
     PKB_TRY(ws->sumsq[i].ensure(static_cast<size_t>(rows) * max_tiles * sizeof(float)));
   }
   const Stage &last = am->stages.back();
-  PKB_TRY(ws->lse_part.ensure(static_cast<size_t>(rows) * (last.n_pad / last.block_n) * sizeof(float2)));
+  PKB_TRY(ws->lse_part.ensure(static_cast<size_t>((rows + kBlockM - 1) / kBlockM) * kBlockM *
+                              (last.n_pad / last.block_n) * sizeof(float2)));
+  PKB_TRY(ws->tile_done.ensure(sizeof(int) * static_cast<size_t>((rows + kBlockM - 1) / kBlockM)));
   return PKB_OK;
 }
 
@@ -396,7 +349,13 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       p.out_f32 = d_out;
       p.ld_f32 = st.out_dim;
       p.row_map = use_row_map ? ws->row_map.as<int32_t>() : nullptr;
-      p.lse_part = (am->softmax_last && mode != kFinalRaw) ? ws->lse_part.as<float2>() : nullptr;
+      // softmax + AM epilogue are fused into this GEMM (no second pass over the output)
+      p.final_mode = am->softmax_last ? (mode == kFinalLoglik ? 2 : (mode == kFinalProb ? 1 : 0)) : 0;
+      p.lse_part = ws->lse_part.as<float2>();
+      p.tile_done = ws->tile_done.as<int>();
+      p.log_prior = am->log_prior.as<float>();
+      p.scale = prob_scale;
+      p.log_floor = static_cast<float>(log(static_cast<double>(static_cast<float>(1.0e-20))));
     }
     PKB_TRY(launch_gemm(c, st.block_n, am->planes, final, &tm_a_hi, &tm_a_lo, &st.tm_w_hi,
                         &st.tm_w_lo, p));
@@ -408,18 +367,10 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       in_sumsq = p.out_sumsq;
       in_sumsq_tiles = p.n_tiles_n;
       in_dim = static_cast<float>(st.out_dim);
-    } else if (p.lse_part != nullptr) {
-      const float log_floor = static_cast<float>(log(static_cast<double>(static_cast<float>(1.0e-20))));
-      const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(c->sm_count) * 16));
-      LaunchScope scope(c, PKB_KERNEL_FINALIZE);
-      finalize_kernel<<<grid, 256, 0, c->stream>>>(d_out, st.out_dim, st.out_dim, p.lse_part,
-                                                   p.n_tiles_n, p.row_map, rows, mode, prob_scale,
-                                                   log_floor, am->log_prior.as<float>());
-      PKB_CUDA(cudaGetLastError());
-    } else if (prob_scale != 1.0f && mode == kFinalLoglik) {
+    } else if (p.final_mode == 0 && prob_scale != 1.0f && mode == kFinalLoglik) {
       const int64_t n = out_rows * st.out_dim;
       const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(c->sm_count) * 8));
-      LaunchScope scope(c, PKB_KERNEL_FINALIZE);
+      LaunchScope scope(c, PKB_KERNEL_MISC);
       scale_kernel<<<grid, 256, 0, c->stream>>>(d_out, n, prob_scale);
       PKB_CUDA(cudaGetLastError());
     }

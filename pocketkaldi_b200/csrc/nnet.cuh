@@ -39,7 +39,7 @@ struct InputView {
 // Per-batch scratch of the forward pass.
 struct Workspace {
   int64_t rows = 0;  // M of every GEMM
-  DevBuf act_hi[2], act_lo[2], sumsq[2], lse_part, row_map;
+  DevBuf act_hi[2], act_lo[2], sumsq[2], lse_part, tile_done, row_map;
   // padded feature planes of the batch pipeline
   DevBuf feat_hi, feat_lo, pad_off;
   void release();

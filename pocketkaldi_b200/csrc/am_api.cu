@@ -231,6 +231,7 @@ struct pkb_batch {
   Workspace ws;
   pkb::PaddedPlanes planes;
   int64_t padded = 0, gemm_rows = 0;
+  std::vector<int64_t> pad_off;  // host copy: first padded row of every utterance
 };
 
 extern "C" {
@@ -342,7 +343,7 @@ int pkb_am_compute(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t
   PKB_CUDA(cudaMemcpyAsync(ws.pad_off.p, pad_off.data(), pad_off.size() * sizeof(int64_t),
                            cudaMemcpyHostToDevice, c->stream));
   const size_t in_bytes = static_cast<size_t>(m.total_frames) * feat_dim * sizeof(float);
-  const size_t out_bytes = static_cast<size_t>(m.total_frames) * am->num_pdfs * sizeof(float);
+  const size_t out_bytes = static_cast<size_t>(rows) * am->num_pdfs * sizeof(float);  // padded rows
   PKB_TRY(am->in_f32.ensure(in_bytes));
   PKB_TRY(am->out_f32.ensure(out_bytes));
   PKB_CUDA(cudaMemcpyAsync(am->in_f32.p, feats, in_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -357,9 +358,10 @@ int pkb_am_compute(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t
   in.rows = rows;
   in.cols = (am->left + am->right + 1) * dp;
   in.pitch_elems = dp;
-  PKB_TRY(pkb::nnet_forward(am, &ws, in, &am->splice_stage, true, pkb::kFinalLoglik, prob_scale,
-                            am->out_f32.as<float>(), m.total_frames));
-  PKB_CUDA(cudaMemcpyAsync(loglik_out, am->out_f32.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  PKB_TRY(pkb::nnet_forward(am, &ws, in, &am->splice_stage, pkb::kFinalLoglik, prob_scale,
+                            am->out_f32.as<float>()));
+  PKB_TRY(pkb::copy_rows_compact(c, loglik_out, am->out_f32.as<float>(), m, pad_off, am->num_pdfs, 0,
+                                 m.total_frames));
   PKB_CUDA(cudaStreamSynchronize(c->stream));  // also covers the pad_off staging vector
   return PKB_OK;
 }
@@ -395,8 +397,7 @@ int pkb_nnet_propagate(pkb_ctx_t *c, pkb_am_t *am, const float *in_host, int row
   in.cols = dp;
   in.pitch_elems = dp;
   const pkb::FinalMode mode = am->softmax_last ? pkb::kFinalProb : pkb::kFinalRaw;
-  PKB_TRY(pkb::nnet_forward(am, &ws, in, &am->stages[0], false, mode, 1.0f, am->out_f32.as<float>(),
-                            rows));
+  PKB_TRY(pkb::nnet_forward(am, &ws, in, &am->stages[0], mode, 1.0f, am->out_f32.as<float>()));
   PKB_CUDA(cudaMemcpyAsync(out, am->out_f32.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   PKB_CUDA(cudaStreamSynchronize(c->stream));
   return PKB_OK;
@@ -428,7 +429,7 @@ int pkb_batch_create(pkb_ctx_t *c, pkb_am_t *am, int n_utts, const int32_t *num_
     if ((rc = b->feats.ensure(std::max<size_t>(4, feat_bytes))) != PKB_OK) break;
     if ((rc = b->sum.ensure(sizeof(double))) != PKB_OK) break;
     if (am) {
-      std::vector<int64_t> pad_off;
+      std::vector<int64_t> &pad_off = b->pad_off;
       pkb::padded_rows(m, am->left, am->right, &pad_off, &b->padded, &b->gemm_rows);
       Workspace &ws = b->ws;
       if ((rc = pkb::workspace_ensure(am, &ws, b->gemm_rows)) != PKB_OK) break;
@@ -438,7 +439,8 @@ int pkb_batch_create(pkb_ctx_t *c, pkb_am_t *am, int n_utts, const int32_t *num_
       if (am->planes == 2 && (rc = ws.feat_lo.ensure(plane_bytes)) != PKB_OK) break;
       if ((rc = ws.pad_off.ensure(std::max<size_t>(8, pad_off.size() * sizeof(int64_t)))) != PKB_OK) break;
       if ((rc = ws.row_map.ensure(std::max<size_t>(4, static_cast<size_t>(b->gemm_rows) * 4))) != PKB_OK) break;
-      if ((rc = b->loglik.ensure(std::max<size_t>(4, static_cast<size_t>(m.total_frames) *
+      // padded-row layout: one output row per GEMM row
+      if ((rc = b->loglik.ensure(std::max<size_t>(4, static_cast<size_t>(b->gemm_rows) *
                                                          am->num_pdfs * sizeof(float)))) != PKB_OK)
         break;
       if (!pad_off.empty() &&
@@ -527,8 +529,8 @@ int pkb_batch_run(pkb_batch_t *b, int stages) {
     in.rows = b->gemm_rows;
     in.cols = (am->left + am->right + 1) * am->feat_dim_pad;
     in.pitch_elems = am->feat_dim_pad;
-    PKB_TRY(pkb::nnet_forward(am, &b->ws, in, &am->splice_stage, true, pkb::kFinalLoglik,
-                              b->prob_scale, b->loglik.as<float>(), b->meta.total_frames));
+    PKB_TRY(pkb::nnet_forward(am, &b->ws, in, &am->splice_stage, pkb::kFinalLoglik, b->prob_scale,
+                              b->loglik.as<float>()));
   }
   return PKB_OK;
 }
@@ -572,6 +574,9 @@ int pkb_batch_get_rows(pkb_batch_t *b, int which, int64_t row0, int64_t n_rows, 
               (long long)(row0 + n_rows), (long long)rows);
   if (n_rows == 0) return PKB_OK;
   PKB_REQUIRE(host_dst, "pkb_batch_get_rows: host_dst is NULL");
+  if (which == PKB_BUF_LOGLIK)  // stored with padded rows: compact per utterance on the way out
+    return pkb::copy_rows_compact(b->c, host_dst, b->loglik.as<float>(), b->meta, b->pad_off,
+                                  b->am->num_pdfs, row0, n_rows);
   PKB_CUDA(cudaMemcpyAsync(host_dst, ptr + row0 * row_bytes, n_rows * row_bytes,
                            cudaMemcpyDeviceToHost, b->c->stream));
   return PKB_OK;
@@ -594,7 +599,11 @@ int pkb_batch_checksum(pkb_batch_t *b, int which, double *sum_out) {
   int64_t rows = 0;
   PKB_TRY(batch_buf(b, which, &ptr, &row_bytes, &rows));
   const int64_t n = rows * static_cast<int64_t>(row_bytes / sizeof(float));
-  PKB_TRY(pkb::launch_checksum(b->c, reinterpret_cast<const float *>(ptr), n, b->sum.as<double>()));
+  if (which == PKB_BUF_LOGLIK)
+    PKB_TRY(pkb::launch_checksum_rows(b->c, b->loglik.as<float>(), b->am->num_pdfs, b->gemm_rows,
+                                      b->ws.row_map.as<int32_t>(), b->sum.as<double>()));
+  else
+    PKB_TRY(pkb::launch_checksum(b->c, reinterpret_cast<const float *>(ptr), n, b->sum.as<double>()));
   PKB_CUDA(cudaMemcpyAsync(sum_out, b->sum.p, sizeof(double), cudaMemcpyDeviceToHost, b->c->stream));
   PKB_CUDA(cudaStreamSynchronize(b->c->stream));
   return PKB_OK;

@@ -98,6 +98,26 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
       : "memory");
 }
 
+// shared -> global bulk tensor store of one {32 cols x 32 rows} FP32 box (clipped at the
+// tensor's edges by the TMA unit)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c_inner,
+                                             int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                    smem_u32(dst)),
@@ -222,7 +242,7 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool 
   L.stage_bytes = planes * (L.a_plane + L.w_plane);
   // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
   // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch
-  L.epi_bytes = final ? 8 * 4096 + 2 * block_n * 4 + 128 * 8 : 4 * planes * 4096;
+  L.epi_bytes = final ? 8 * 8192 + 2 * block_n * 4 + 128 * 8 : 4 * planes * 4096;
   uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */ - L.epi_bytes;
   L.stages = avail / L.stage_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
@@ -255,7 +275,7 @@ template <int BN, int PLANES, bool FINAL>
 __global__ void __launch_bounds__(num_threads(FINAL), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-            const GemmParams p) {
+            const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const SmemLayout L = smem_layout(BN, PLANES, FINAL);
   uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -271,6 +291,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   const uint32_t S = L.stages;
 
   if (warp == 0 && lane == 0) {
+    if (FINAL) tma_prefetch_desc(&tm_out);
     tma_prefetch_desc(&tm_a_hi);
     tma_prefetch_desc(&tm_w_hi);
     if (PLANES == 2) {
@@ -367,10 +388,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     // per-warp staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7);
     // rows are written by their owner lane and read back 4 rows per instruction so that
     // every global store covers whole 128-byte lines
-    uint8_t *stg = smem + L.epi_off + (FINAL ? (warp - 4) * 4096 : q * (PLANES * 4096));
+    uint8_t *stg = smem + L.epi_off + (FINAL ? (warp - 4) * 8192 : q * (PLANES * 4096));
     const uint32_t stg_w = smem_u32(stg) + lane * 128;          // this lane's row
     // grouped schedule: this CTA's column tile never changes, keep its bias / log-prior in smem
-    float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + 8 * 4096);
+    float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + 8 * 8192);
     float *s_lp = s_bias + BN;
     constexpr int kEpiThreads = 32 * epi_warps(FINAL);
     if (FINAL && p.group_sched) {
@@ -382,6 +403,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       named_bar_sync(1, kEpiThreads);
     }
     const int t_row = lane >> 3, t_chunk = lane & 7;            // transposed read role
+    uint32_t store_seq = 0;  // staging-buffer parity of this warp's TMA stores
     int m_blk, n_blk;
     for (int it = 0; get_tile(p, it, m_blk, n_blk); ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
@@ -558,9 +580,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           }
         }
         if (dbg_on) tk4 = clock64();
-        // ---- pass 2: final values, staged and written as whole 128-byte lines
-        int dest = -1;
-        if (row_ok) dest = p.row_map ? p.row_map[row] : row;
+        // ---- pass 2: final values -> swizzled staging tile -> TMA bulk tensor store.
+        //      Two staging buffers per warp: the store of chunk c drains while chunk c+1 is
+        //      computed; the TMA unit clips rows >= M and columns >= N_valid.
         const bool vec_ok = (p.ld_f32 & 3) == 0;
         const float floor_v = p.log_floor, sc = p.scale;
 #pragma unroll 1
@@ -569,11 +591,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           const int nvalid = p.N_valid - col0;
           if (nvalid <= 0) break;
           uint32_t v[32];
-          long long u0 = 0, u1 = 0, u2 = 0;
-          if (dbg_on) u0 = clock64();
           tmem_ld32(taddr + cbase + c * 32, v);
           tmem_ld_wait();
-          if (dbg_on) u1 = clock64();
           float z[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -591,7 +610,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           } else if (p.final_mode == 2) {  // scaled log-likelihood (src/am.cc:106-112, decodable.cc:15)
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              // log_prior is padded to N_pad, so the vector load is always in bounds
               const float4 lp = *reinterpret_cast<const float4 *>(s_lp + cbase + c * 32 + i);
               z[i + 0] = (fmaxf(z[i + 0] - lse, floor_v) - lp.x) * sc;
               z[i + 1] = (fmaxf(z[i + 1] - lse, floor_v) - lp.y) * sc;
@@ -600,32 +618,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             }
           }
           if (vec_ok) {
+            const uint32_t buf = (store_seq & 1) * 4096;
+            // the store issued two chunks ago has finished reading this buffer
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              st_shared_v4(stg_w + ((j ^ (lane & 7)) << 4), __float_as_uint(z[4 * j]),
+              st_shared_v4(stg_w + buf + ((j ^ (lane & 7)) << 4), __float_as_uint(z[4 * j]),
                            __float_as_uint(z[4 * j + 1]), __float_as_uint(z[4 * j + 2]),
                            __float_as_uint(z[4 * j + 3]));
+            fence_proxy_async_smem();
             __syncwarp();
-            if (dbg_on) u2 = clock64();
-            const bool col_ok = t_chunk * 4 < nvalid;
-            float *gbase = p.out_f32 + col0 + t_chunk * 4;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 4 * i + t_row;
-              const int d = __shfl_sync(0xffffffffu, dest, rr);
-              if (d >= 0 && col_ok) {
-                const uint32_t src = smem_u32(stg) + rr * 128 + ((t_chunk ^ (rr & 7)) << 4);
-                *reinterpret_cast<uint4 *>(gbase + static_cast<size_t>(d) * p.ld_f32) = ld_shared_v4(src);
-              }
+            if (lane == 0) {
+              tma_store_2d(&tm_out, smem_u32(stg) + buf, col0, wrow0);
+              tma_store_commit();
             }
-            __syncwarp();
-            if (dbg_on) {
-              const long long u3 = clock64();
-              p.dbg[static_cast<size_t>(blockIdx.x) * 8 + 6] += u1 - u0;
-              p.dbg[static_cast<size_t>(blockIdx.x) * 8 + 7] += u3 - u2;
-            }
-          } else if (dest >= 0) {
-            float *dst = p.out_f32 + static_cast<size_t>(dest) * p.ld_f32 + col0;
+            ++store_seq;
+          } else if (row_ok) {
+            float *dst = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + col0;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (i < nvalid) dst[i] = z[i];
@@ -646,6 +656,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
       }
     }
+    // shared memory must stay valid until the last bulk stores have read it
+    if (FINAL && lane == 0) tma_store_wait_read<0>();
+    (void)store_seq;
   }
 
   tc_fence_before();
@@ -676,6 +689,10 @@ EncodeTiledFn get_encode_fn() {
 template <int BN, int PLANES, bool FINAL>
 int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const CUtensorMap *w_hi,
                const CUtensorMap *w_lo, const GemmParams &p) {
+  // FP32 output map of the final stage (hidden stages pass a dummy copy of the A map)
+  CUtensorMap out_map = *a_hi;
+  if (FINAL && (p.ld_f32 & 3) == 0)
+    PKB_TRY(make_output_map(&out_map, p.out_f32, p.N_valid, p.M));
   const SmemLayout L = smem_layout(BN, PLANES, FINAL);
   auto kern = gemm_kernel<BN, PLANES, FINAL>;
   PKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -705,11 +722,11 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
     // for each other: a cooperative launch guarantees that all CTAs are co-resident
     PKB_CUDA(cudaMemsetAsync(p.tile_done, 0, sizeof(int) * ((p.M + kBlockM - 1) / kBlockM), c->stream));
     CUtensorMap m0 = *a_hi, m1 = *a_lo, m2 = *w_hi, m3 = *w_lo;
-    void *args[] = {&m0, &m1, &m2, &m3, &pp};
+    void *args[] = {&m0, &m1, &m2, &m3, &out_map, &pp};
     PKB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid),
                                          dim3(num_threads(FINAL)), args, L.total, c->stream));
   } else {
-    kern<<<grid, num_threads(FINAL), L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, pp);
+    kern<<<grid, num_threads(FINAL), L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, out_map, pp);
   }
   PKB_CUDA(cudaGetLastError());
   }
@@ -722,8 +739,8 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
     for (int b = 0; b < grid; ++b)
       for (int k = 0; k < 8; ++k) s[k] += h[8 * b + k];
     const double n = s[5] > 0 ? s[5] : 1;
-    fprintf(stderr, "[pkb gemm final] tiles/cta=%.0f cycles/tile: wait_acc=%.0f pass1=%.0f sync=%.0f combine=%.0f pass2=%.0f (tmem_ld=%.0f store=%.0f)\n",
-            n / grid, s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n, s[6] / n, s[7] / n);
+    fprintf(stderr, "[pkb gemm final] tiles/cta=%.0f cycles/tile: wait_acc=%.0f pass1=%.0f sync=%.0f combine=%.0f pass2=%.0f\n",
+            n / grid, s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n);
   }
   return PKB_OK;
 }
@@ -749,6 +766,27 @@ int make_tensor_map(CUtensorMap *map, const void *base, uint64_t cols, uint64_t 
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) cols=%llu rows=%llu pitch=%llu", (int)r,
               (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_bytes);
+    return PKB_ERR_CUDA;
+  }
+  return PKB_OK;
+}
+
+int make_output_map(CUtensorMap *map, const float *base, uint64_t cols, uint64_t rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return PKB_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed (CUresult %d) cols=%llu rows=%llu", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows);
     return PKB_ERR_CUDA;
   }
   return PKB_OK;

@@ -23,7 +23,9 @@ constexpr int kUmmaK = 16;     // K of one tcgen05.mma kind::f16
 //                                                          preceding NormalizeLayer, else 1
 //   hidden   : y = relu ? max(z, 0) : z ; optional per-row sum of y^2 (for a following
 //              NormalizeLayer); stored as BF16 hi (+ lo = bf16(y - hi) in BF16X3)
-//   final    : FP32 output at row_map[row] (skipped when < 0). With a SoftmaxLayer the CTAs that
+//   final    : FP32 output, row m of the GEMM -> row m of the output (the caller keeps the
+//              padded-row layout and compacts per utterance when copying out). Tiles leave the
+//              SM through shared memory and TMA bulk tensor stores. With a SoftmaxLayer the CTAs that
 //              own the column tiles of one row block exchange per-row (max, sum exp) partials
 //              through global memory while the accumulators stay in TMEM, then write
 //              softmax(z) or prob_scale * (max(log softmax(z), log 1e-20) - log_prior) once --
@@ -44,9 +46,8 @@ struct GemmParams {
   int relu;
   __nv_bfloat16 *out_hi, *out_lo;  // [M][ld_out]
   int ld_out;
-  float *out_f32;      // final: [rows][ld_f32]
+  float *out_f32;      // final: [M][ld_f32], GEMM row m -> output row m (padded-row layout)
   int ld_f32;
-  const int32_t *row_map;  // final: [M] destination row or -1; nullptr = identity
   // final_mode: 0 raw logits, 1 softmax probabilities, 2 scale*(max(log softmax, log_floor) - log_prior)
   int final_mode;
   float2 *lse_part;    // final softmax: [M][n_tiles_n] (max, sum exp) exchanged between column tiles
@@ -66,6 +67,10 @@ int make_tensor_map(CUtensorMap *map, const void *base, uint64_t cols, uint64_t 
 int launch_gemm(Ctx *c, int block_n, int planes, bool final, const CUtensorMap *a_hi,
                 const CUtensorMap *a_lo, const CUtensorMap *w_hi, const CUtensorMap *w_lo,
                 const GemmParams &p);
+
+// FP32 [rows][cols] output map for the final stage's TMA stores: box {32 cols, 32 rows},
+// 128-byte swizzle. Needs cols % 4 == 0 (16-byte row pitch).
+int make_output_map(CUtensorMap *map, const float *base, uint64_t cols, uint64_t rows);
 
 int gemm_max_smem_bytes(int block_n, int planes);
 

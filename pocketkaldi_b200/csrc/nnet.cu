@@ -301,8 +301,7 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
 }
 
 int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *first,
-                 bool use_row_map, FinalMode mode, float prob_scale, float *d_out,
-                 int64_t out_rows) {
+                 FinalMode mode, float prob_scale, float *d_out) {
   Ctx *c = am->c;
   const int64_t rows = ws->rows;
   if (rows == 0) return PKB_OK;
@@ -348,7 +347,6 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
     } else {
       p.out_f32 = d_out;
       p.ld_f32 = st.out_dim;
-      p.row_map = use_row_map ? ws->row_map.as<int32_t>() : nullptr;
       // softmax + AM epilogue are fused into this GEMM (no second pass over the output)
       p.final_mode = am->softmax_last ? (mode == kFinalLoglik ? 2 : (mode == kFinalProb ? 1 : 0)) : 0;
       p.lse_part = ws->lse_part.as<float2>();
@@ -368,13 +366,68 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       in_sumsq_tiles = p.n_tiles_n;
       in_dim = static_cast<float>(st.out_dim);
     } else if (p.final_mode == 0 && prob_scale != 1.0f && mode == kFinalLoglik) {
-      const int64_t n = out_rows * st.out_dim;
+      const int64_t n = rows * st.out_dim;
       const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(c->sm_count) * 8));
       LaunchScope scope(c, PKB_KERNEL_MISC);
       scale_kernel<<<grid, 256, 0, c->stream>>>(d_out, n, prob_scale);
       PKB_CUDA(cudaGetLastError());
     }
   }
+  return PKB_OK;
+}
+
+int copy_rows_compact(Ctx *c, void *host_dst, const float *d_padded, const BatchMeta &m,
+                      const std::vector<int64_t> &pad_off, int cols, int64_t frame0, int64_t n) {
+  if (n <= 0) return PKB_OK;
+  // first utterance whose frame range reaches past frame0
+  int u = static_cast<int>(std::upper_bound(m.frame_off.begin(), m.frame_off.end(), frame0) -
+                           m.frame_off.begin()) - 1;
+  if (u < 0) u = 0;
+  const int64_t end = frame0 + n;
+  char *dst = static_cast<char *>(host_dst);
+  const size_t row_bytes = static_cast<size_t>(cols) * sizeof(float);
+  for (; u < m.n_utts && m.frame_off[u] < end; ++u) {
+    const int64_t a = std::max<int64_t>(frame0, m.frame_off[u]);
+    const int64_t b = std::min<int64_t>(end, m.frame_off[u + 1]);
+    if (b <= a) continue;
+    const int64_t prow = pad_off[u] + (a - m.frame_off[u]);
+    PKB_CUDA(cudaMemcpyAsync(dst + (a - frame0) * row_bytes,
+                             reinterpret_cast<const char *>(d_padded) + prow * row_bytes,
+                             (b - a) * row_bytes, cudaMemcpyDeviceToHost, c->stream));
+  }
+  return PKB_OK;
+}
+
+namespace {
+__global__ void checksum_rows_kernel(const float *__restrict__ x, int cols, int64_t rows,
+                                     const int32_t *__restrict__ row_map, double *sum) {
+  double acc = 0.0;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    if (row_map[r] < 0) continue;
+    const float *row = x + r * cols;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) acc += static_cast<double>(row[j]);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += s[i];
+    atomicAdd(sum, t);
+  }
+}
+}  // namespace
+
+int launch_checksum_rows(Ctx *c, const float *d, int cols, int64_t rows, const int32_t *row_map,
+                         double *d_sum) {
+  PKB_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), c->stream));
+  if (rows == 0) return PKB_OK;
+  const int grid = static_cast<int>(std::min<int64_t>(rows, static_cast<int64_t>(c->sm_count) * 16));
+  LaunchScope scope(c, PKB_KERNEL_MISC);
+  checksum_rows_kernel<<<grid, 256, 0, c->stream>>>(d, cols, rows, row_map, d_sum);
+  PKB_CUDA(cudaGetLastError());
   return PKB_OK;
 }
 

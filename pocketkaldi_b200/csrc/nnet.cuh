@@ -82,10 +82,20 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
 int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows);
 
 // Runs every stage. `first` selects the weights of stage 0 (am->stages[0] or
-// am->splice_stage). Output rows are scattered through ws->row_map when
-// use_row_map (padded batch), else written 1:1.
+// am->splice_stage). d_out is [ws->rows][out_dim]: GEMM row m -> output row m. For a padded
+// batch the rows of utterance u start at pad_off[u] and the (left+right) rows between two
+// utterances hold garbage; copy_rows_compact() removes them on the way out.
 int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *first,
-                 bool use_row_map, FinalMode mode, float prob_scale, float *d_out, int64_t out_rows);
+                 FinalMode mode, float prob_scale, float *d_out);
+
+// Device (padded rows) -> host (compact frames) copy of frames [frame0, frame0 + n): one
+// cudaMemcpyAsync per utterance touched.
+int copy_rows_compact(Ctx *c, void *host_dst, const float *d_padded, const BatchMeta &m,
+                      const std::vector<int64_t> &pad_off, int cols, int64_t frame0, int64_t n);
+
+// Sum over the valid rows (row_map[m] >= 0) of a padded [rows][cols] matrix, in double.
+int launch_checksum_rows(Ctx *c, const float *d, int cols, int64_t rows, const int32_t *row_map,
+                         double *d_sum);
 
 // float [F][dim] -> padded BF16 planes with replicated edge frames + row map.
 int launch_pack_padded(Ctx *c, const float *d_feats, const BatchMeta &m, int dim, int dim_pad,

@@ -140,22 +140,10 @@ def barrier(dist, local):
         torch.cuda.synchronize()
 
 
-def max_over_ranks(dist, local, value):
-    if dist is None:
-        return value
-    import torch
-    t = torch.tensor([value], dtype=torch.float64, device="cuda:%d" % local)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
-
-
-def sum_over_ranks(dist, local, value):
-    if dist is None:
-        return value
-    import torch
-    t = torch.tensor([value], dtype=torch.float64, device="cuda:%d" % local)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+def reduce_timing(dist, local, ms, frames):
+    """(max over ranks of the device-timed ms, sum over ranks of frames)."""
+    from pocketkaldi_b200 import sharding
+    return sharding.reduce_timing(dist, ms, frames, device="cuda:%d" % local if dist else None)
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -248,7 +236,8 @@ def run_gpu_arm(args, cfg):
         am = pk.AcousticModel(ctx, prec).from_layers(layers, prior, 5, 5)
     stages = pk.STAGE_ALL if cfg["nnet"] else (pk.STAGE_FBANK | pk.STAGE_CMVN)
     batch = pk.Batch(ctx, [SAMPLES_10S] * n_utts, g, am, prob_scale=0.1)
-    batch.synth_pcm(1234, rank * n_utts)
+    from pocketkaldi_b200 import sharding
+    batch.synth_pcm(1234, int(sharding.weak_scaling_ids(rank, n_utts)[0]))
     ctx.sync()
     frames = batch.total_frames
 
@@ -268,8 +257,7 @@ def run_gpu_arm(args, cfg):
     clocks = sampler.stop() if sampler else None
     prof = ctx.profile_get()
     ctx.profile_enable(False)
-    ms_max = max_over_ranks(dist, local, ms)
-    total_frames = sum_over_ranks(dist, local, float(frames))
+    ms_max, total_frames = reduce_timing(dist, local, ms, frames)
     value = total_frames * args.steps / (ms_max * 1e-3)
     checksum = batch.checksum(pk.BUF_LOGLIK if cfg["nnet"] else pk.BUF_FEATS)
 
@@ -386,8 +374,7 @@ def run_e2e(args, cfg, ctx, am, g, rank, local, dist, n_utts):
         step()
     ms = ctx.timer_stop()
     barrier(dist, local)
-    ms_max = max_over_ranks(dist, local, ms)
-    frames = sum_over_ranks(dist, local, float(cb.total_frames * n_chunks))
+    ms_max, frames = reduce_timing(dist, local, ms, cb.total_frames * n_chunks)
     fin = bool(np.isfinite(pin_out.array[::997]).all())
     cb.close()
     pin_in.free()

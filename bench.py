@@ -42,6 +42,8 @@ CONFIGS = {
               name="config3: 4096 utts x 10 s, splice+-5 -> 6x1024 ReLU DNN -> 3000 pdfs"),
     "4": dict(utts=1024, hidden=7, width=2048, pdfs=8000, nnet=True,
               name="config4 shard: 1024 utts x 10 s per GPU, splice+-5 -> 7x2048 ReLU DNN -> 8000 pdfs"),
+    "5": dict(utts=64, hidden=6, width=1024, pdfs=3000, nnet=True, stream=True,
+              name="config5: 64 concurrent streams, 160 ms chunks (2560 samples), fbank+CMVN+6x1024->3000 nnet"),
 }
 
 
@@ -417,6 +419,73 @@ def parity_sample(cfg, batch, layers, prior, g):
     return out
 
 
+def run_stream_arm(args, cfg):
+    """BASELINE config 5: chunk latency from "chunk in pinned host memory" to "log-likelihoods in
+    pinned host memory" (host wall clock around the synchronous pkb_stream_push_i16)."""
+    import pocketkaldi_b200 as pk
+    from pocketkaldi_b200.binding import PinnedArray
+    from pocketkaldi_b200.synth import synth_global_cmvn, synth_pcm
+    rank, world, local, dist = dist_setup(args.gpus)
+    ctx = pk.Context(local)
+    g = synth_global_cmvn()
+    prec = pk.PREC_BF16X3 if args.precision == "bf16x3" else pk.PREC_BF16
+    S, chunk = args.utts or cfg["utts"], 2560
+    layers = make_layers(cfg)
+    prior = np.full(cfg["pdfs"], 1.0 / cfg["pdfs"], np.float32)
+    am = pk.AcousticModel(ctx, prec).from_layers(layers, prior, 5, 5)
+    st = pk.Stream(ctx, am, S, chunk, g, 0.1)
+    n_chunks = args.warmup + args.steps
+    pin_in = PinnedArray((S, chunk), np.int16)
+    pin_out = PinnedArray((S, st.max_frames, cfg["pdfs"]), np.float32)
+    audio = synth_pcm(1234, np.arange(S) + rank * S, chunk * 8)
+    lat, frames = [], 0
+    ctx.profile_reset()
+    barrier(dist, local)
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_all0 = None
+    for k in range(n_chunks):
+        pin_in.array[:] = audio[:, (k % 8) * chunk:((k % 8) + 1) * chunk]
+        if k == args.warmup:
+            ctx.profile_reset()
+            t_all0 = time.perf_counter()
+        t0 = time.perf_counter()
+        o = st.push(pin_in.array, out=pin_out.array)
+        t1 = time.perf_counter()
+        if k >= args.warmup:
+            lat.append((t1 - t0) * 1e3)
+            frames += o.shape[1] * S
+    total_ms = (time.perf_counter() - t_all0) * 1e3
+    barrier(dist, local)
+    clocks = sampler.stop() if sampler else None
+    prof = ctx.profile_get()
+    ms_max, frames_all = reduce_timing(dist, local, total_ms, frames)
+    lat = np.array(lat)
+    if rank == 0:
+        value = frames_all / (ms_max * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if prec == pk.PREC_BF16 else "bf16x3", "data": "synthetic",
+            "config": {"workload": cfg["name"], "streams_per_gpu": S, "chunk_samples": chunk,
+                       "timing": "host wall clock around the synchronous push (H2D + kernels + D2H)"},
+            "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                           "mean": float(lat.mean()), "max": float(lat.max())},
+            "rtfx": value / 100.0,
+            "e2e": {"value": value, "unit": "frames/s",
+                    "h2d_bytes_per_step": int(pin_in.array.nbytes),
+                    "d2h_bytes_per_step": int(S * (chunk // 160) * cfg["pdfs"] * 4)},
+            "gpu_launches": int(sum(v[0] for v in prof.values())),
+            "clocks": clocks, "device": ctx.device_name,
+        }
+        print(json.dumps(line), flush=True)
+    st.close()
+    am.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -434,6 +503,8 @@ def main():
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference_arm(args, cfg)
+    elif cfg.get("stream"):
+        run_stream_arm(args, cfg)
     else:
         run_gpu_arm(args, cfg)
 

@@ -19,6 +19,7 @@ from .binding import (  # noqa: F401
     AcousticModel,
     Decodable,
     Batch,
+    Stream,
     build_library,
     load_library,
     PREC_BF16,

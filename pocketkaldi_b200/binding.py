@@ -477,3 +477,45 @@ class Batch:
         s = C.c_double(0)
         _check(self.ctx.lib.pkb_batch_checksum(self.h, which, C.byref(s)))
         return s.value
+
+
+class Stream:
+    """pkb_stream_t: n_streams audio streams advancing in lock step with carried state
+    (PCM tail, CMVN running sums + ring, splice context). No reference equivalent exists; the
+    contract is: concatenated outputs == whole-utterance outputs."""
+
+    def __init__(self, ctx, am, n_streams, chunk_samples, global_stats, prob_scale=1.0):
+        self.ctx, self.am = ctx, am
+        self.n_streams, self.chunk = n_streams, chunk_samples
+        self.h = _VP()
+        _check(ctx.lib.pkb_stream_create(ctx.h, am.h, n_streams, chunk_samples, _f32(global_stats),
+                                         prob_scale, C.byref(self.h)))
+        self.max_frames = ctx.lib.pkb_stream_max_frames(self.h)
+        self.P = am.num_pdfs()
+        self.out = np.empty((n_streams, self.max_frames, self.P), np.float32)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.pkb_stream_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push(self, pcm, out=None):
+        """pcm: int16 [n_streams][chunk]. Returns a view [n_streams][frames][P] (frames may be 0)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        assert pcm.shape == (self.n_streams, self.chunk)
+        out = self.out if out is None else out
+        n = C.c_int32(0)
+        _check(self.ctx.lib.pkb_stream_push_i16(self.h, pcm.ctypes.data, out.ctypes.data, C.byref(n)))
+        return out[:, :n.value]
+
+    def flush(self, out=None):
+        out = self.out if out is None else out
+        n = C.c_int32(0)
+        _check(self.ctx.lib.pkb_stream_flush(self.h, out.ctypes.data, C.byref(n)))
+        return out[:, :n.value]

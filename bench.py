@@ -341,51 +341,72 @@ def run_gpu_arm(args, cfg):
 
 def run_e2e(args, cfg, ctx, am, g, rank, local, dist, n_utts):
     """PCM in pinned host memory -> H2D -> hot path -> D2H of the result into pinned host
-    memory, chunk by chunk through the batch API, all inside the timed region."""
+    memory, chunk by chunk through the batch API, all inside the timed region. Two contexts
+    (two CUDA streams, each with its own model copy and chunk batch) alternate so that the
+    D2H copy of chunk i overlaps the H2D + kernels of chunk i+1."""
     import pocketkaldi_b200 as pk
     from pocketkaldi_b200.binding import PinnedArray
     from pocketkaldi_b200.synth import synth_pcm
     chunk = min(args.e2e_chunk, n_utts)
-    n_chunks = (n_utts + chunk - 1) // chunk
-    if n_utts % chunk:
-        n_chunks = n_utts // chunk  # whole chunks only; the metric is a rate
-    n_chunks = max(n_chunks, 1)
+    n_chunks = max(n_utts // chunk, 1)  # whole chunks only; the metric is a rate
     stages = pk.STAGE_ALL if cfg["nnet"] else (pk.STAGE_FBANK | pk.STAGE_CMVN)
     which = pk.BUF_LOGLIK if cfg["nnet"] else pk.BUF_FEATS
-    cb = pk.Batch(ctx, [SAMPLES_10S] * chunk, g, am, prob_scale=0.1)
     out_cols = cfg["pdfs"] if cfg["nnet"] else 40
-    pin_in = PinnedArray((chunk * SAMPLES_10S,), np.int16)
-    pin_out = PinnedArray((cb.total_frames, out_cols), np.float32)
-    pin_in.array[:] = synth_pcm(1234, np.arange(chunk) + rank * n_utts, SAMPLES_10S).reshape(-1)
-    h2d = pin_in.array.nbytes * n_chunks
-    d2h = pin_out.array.nbytes * n_chunks
+    lanes = []
+    for i in range(2):
+        c = ctx if i == 0 else pk.Context(local)
+        a = am
+        if cfg["nnet"] and i == 1:
+            prec = pk.PREC_BF16X3 if args.precision == "bf16x3" else pk.PREC_BF16
+            a = pk.AcousticModel(c, prec).from_layers(
+                make_layers(cfg), np.full(cfg["pdfs"], 1.0 / cfg["pdfs"], np.float32), 5, 5)
+        cb = pk.Batch(c, [SAMPLES_10S] * chunk, g, a, prob_scale=0.1)
+        pin_in = PinnedArray((chunk * SAMPLES_10S,), np.int16)
+        pin_out = PinnedArray((cb.total_frames, out_cols), np.float32)
+        pin_in.array[:] = synth_pcm(1234, np.arange(chunk) + rank * n_utts + i * chunk,
+                                    SAMPLES_10S).reshape(-1)
+        lanes.append((c, a, cb, pin_in, pin_out))
+    h2d = lanes[0][3].array.nbytes * n_chunks
+    d2h = lanes[0][4].array.nbytes * n_chunks
 
     def step():
-        for _ in range(n_chunks):
+        for k in range(n_chunks):
+            c, a, cb, pin_in, pin_out = lanes[k & 1]
+            c.sync()  # this lane's previous chunk has fully landed in its pinned buffer
             cb.set_pcm(pin_in.array)
             cb.run(stages)
             cb.get_rows_async(which, 0, cb.total_frames, pin_out.array)
-        ctx.sync()
+        for lane in lanes:
+            lane[0].sync()
 
     for _ in range(min(args.warmup, 2)):
         step()
     barrier(dist, local)
     steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
     ctx.timer_start()
     for _ in range(steps):
         step()
     ms = ctx.timer_stop()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = max(ms, wall_ms)  # two streams: the host wall clock covers both lanes
     barrier(dist, local)
-    ms_max, frames = reduce_timing(dist, local, ms, cb.total_frames * n_chunks)
-    fin = bool(np.isfinite(pin_out.array[::997]).all())
-    cb.close()
-    pin_in.free()
-    pin_out.free()
+    ms_max, frames = reduce_timing(dist, local, ms, lanes[0][2].total_frames * n_chunks)
+    fin = bool(np.isfinite(lanes[0][4].array[::997]).all() and np.isfinite(lanes[1][4].array[::997]).all())
+    for i, (c, a, cb, pin_in, pin_out) in enumerate(lanes):
+        cb.close()
+        pin_in.free()
+        pin_out.free()
+        if i == 1:
+            if cfg["nnet"]:
+                a.close()
+            c.close()
     return {"value": frames * steps / (ms_max * 1e-3), "unit": "frames/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
             "ms_per_step": ms_max / steps, "chunk_utts": chunk, "chunks_per_step": n_chunks,
-            "finite": fin,
-            "api": "pkb_batch_set_pcm_i16 + pkb_batch_run + pkb_batch_get_rows (pinned host buffers)"}
+            "finite": fin, "timing": "host wall clock over both streams (>= the CUDA-event time of stream 0)",
+            "api": "2 x (pkb_batch_set_pcm_i16 + pkb_batch_run + pkb_batch_get_rows), pinned host "
+                   "buffers, two contexts alternating so D2H overlaps the next chunk"}
 
 
 def parity_sample(cfg, batch, layers, prior, g):

@@ -216,6 +216,11 @@ __device__ __forceinline__ int ld_relaxed(const int *p) {
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -537,40 +542,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             run_sum = run_sum * exp2f_fast((run_max - nm) * kLog2e) + acc;
             run_max = nm;
           }
-          // (1) fold the two column halves of this CTA in shared memory
-          float2 *s_half = reinterpret_cast<float2 *>(s_lp + BN);  // [128]
+          // (1) publish one (max, sum) per row and column half-tile, row-fastest so that every
+          //     warp-wide access to the exchange buffer is one contiguous 256-byte segment
           const int rit = q * 32 + lane;  // row inside the tile
-          if (chalf == 1) s_half[rit] = make_float2(run_max, run_sum);
+          const int n_parts = 2 * p.n_tiles_n;
+          float2 *xbase = p.lse_part + static_cast<size_t>(m_blk) * n_parts * kBlockM;
+          __stcg(&xbase[(2 * n_blk + chalf) * kBlockM + rit], make_float2(run_max, run_sum));
           if (dbg_on) tk2 = clock64();
           named_bar_sync(1, kEpiThreads);
-          // (2) publish one (max, sum) per row and column tile, row-fastest so that every
-          //     warp-wide access to the exchange buffer is one contiguous 256-byte segment
-          float2 *xbase = p.lse_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
-          if (chalf == 0) {
-            const float2 o = s_half[rit];
-            const float nm = fmaxf(run_max, o.x);
-            const float sm = run_sum * exp2f_fast((run_max - nm) * kLog2e) +
-                             o.y * exp2f_fast((o.x - nm) * kLog2e);
-            __stcg(&xbase[n_blk * kBlockM + rit], make_float2(nm, sm));
-          }
-          named_bar_sync(1, kEpiThreads);
-          // (3) one thread makes the CTA's partials visible device-wide, signals, and waits for
-          //     the peer CTAs of this row block (relaxed polling, a single acquire at the end)
+          // (2) one thread releases the CTA's partials device-wide (the named barrier orders the
+          //     other threads' stores before it), then waits for the peer CTAs of this row block:
+          //     relaxed polling, one acquire at the end
           if (warp == 4 && lane == 0) {
-            __threadfence();
             red_release_add(p.tile_done + m_blk, 1);
             const long long t0 = clock64();
             while (ld_relaxed(p.tile_done + m_blk) < p.n_tiles_n) {
               if (clock64() - t0 > 4000000000ll) __trap();
             }
-            __threadfence();
+            (void)ld_acquire(p.tile_done + m_blk);
           }
           named_bar_sync(1, kEpiThreads);
           if (dbg_on) tk3 = clock64();
-          // (4) combine the n_tiles_n partials of this row (coalesced, independent loads)
+          // (3) combine the partials of this row (coalesced, independent loads)
           {
             float mx = -INFINITY, ssum = 0.0f;
-            for (int j = 0; j < p.n_tiles_n; ++j) {
+            for (int j = 0; j < n_parts; ++j) {
               const float2 e = __ldcg(&xbase[j * kBlockM + rit]);
               const float nm = fmaxf(mx, e.x);
               ssum = ssum * exp2f_fast((mx - nm) * kLog2e) + e.y * exp2f_fast((e.x - nm) * kLog2e);

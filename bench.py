@@ -228,7 +228,7 @@ def run_gpu_arm(args, cfg):
     peaks = load_peaks()
     ctx = pk.Context(local)
     g = synth_global_cmvn()
-    prec = pk.PREC_BF16X3 if args.precision == "bf16x3" else pk.PREC_BF16
+    prec = {"bf16": pk.PREC_BF16, "bf16x3": pk.PREC_BF16X3, "fp16": pk.PREC_FP16}[args.precision]
     n_utts = args.utts or cfg["utts"]
     am = None
     layers = prior = None
@@ -270,8 +270,20 @@ def run_gpu_arm(args, cfg):
     front_gbs = 480.0 * frames * args.steps / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else None
     if cfg["nnet"]:
         achieved = flops_per_frame(cfg) * frames * args.steps / (gemm_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1d_gemm_traffic.json")
+        if args.config == "3" and os.path.exists(tpath):
+            # dram__bytes_read+write of the 7 GEMM launches of one step (ncu --set full at 512
+            # utterances, linear in frames), averaged per launch like `achieved`
+            traffic = json.load(open(tpath))["dram_bytes_per_frame"] * frames / (cfg["hidden"] + 1)
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor_sustained"],
-                    "unit": "TFLOP/s", "frac": achieved / peaks["tensor_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / peaks["tensor_sustained"], "traffic": traffic,
+                    "traffic_note": "bytes per GEMM launch (mean of the 7 layers); algorithmic "
+                                    "activation + output bytes are the same 36.2 KB/frame/step",
+                    "hidden_layers_tflops": (flops_per_frame(cfg) - 2 * cfg["width"] * cfg["pdfs"]) * frames
+                                            * args.steps / (prof["gemm"][1] * 1e-3) / 1e12,
+                    "output_layer_tflops": 2 * cfg["width"] * cfg["pdfs"] * frames * args.steps
+                                           / (prof["gemm_final"][1] * 1e-3) / 1e12,
                     "kernel": "gemm_kernel (tcgen05, all %d layers)" % (cfg["hidden"] + 1),
                     "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["src"],
                     "avg_launch_ms": gemm_ms / max(gemm_launches, 1)}
@@ -289,6 +301,7 @@ def run_gpu_arm(args, cfg):
     # ---- CPU baseline (rank 0, N=1 only): the reference on this host's cores + parity sample
     cpu = None
     parity = None
+    other_modes = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         n_ref = reference_sample_size(cfg, cores)
@@ -299,7 +312,11 @@ def run_gpu_arm(args, cfg):
                    "sample": "%d synthetic 10 s utterances (%d frames), std::thread pool, oracle/_ref -O2"
                              % (n_ref, f_ref),
                    "single_thread_value": f1 / sec1}
-            parity = parity_sample(cfg, batch, layers, prior, g)
+            ref_pack = reference_outputs(cfg, g)
+            parity = parity_sample(cfg, batch, ref_pack)
+            if cfg["nnet"]:
+                batch.close()  # free HBM before the secondary modes allocate
+                other_modes = measure_other_modes(args, cfg, ctx, g, ref_pack, args.precision)
         except Exception as e:  # the reference library is test infrastructure; report, don't die
             cpu = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference",
                    "sample": "unavailable: %s" % e}
@@ -309,7 +326,7 @@ def run_gpu_arm(args, cfg):
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if prec == pk.PREC_BF16 else "bf16x3", "data": "synthetic",
+            "dtype": args.precision, "data": "synthetic",
             "config": {"workload": cfg["name"], "utts_per_gpu": n_utts, "frames_per_gpu": frames,
                        "l2": "inputs larger than L2 (PCM %.2f GB, activations > 1 GB per layer)"
                              % (batch.total_samples * 2 / 1e9),
@@ -328,6 +345,7 @@ def run_gpu_arm(args, cfg):
             "clocks": clocks,
             "checksum": checksum,
             "parity": parity,
+            "precision_modes": other_modes,
             "device": ctx.device_name,
         }
         print(json.dumps(line), flush=True)
@@ -357,7 +375,7 @@ def run_e2e(args, cfg, ctx, am, g, rank, local, dist, n_utts):
         c = ctx if i == 0 else pk.Context(local)
         a = am
         if cfg["nnet"] and i == 1:
-            prec = pk.PREC_BF16X3 if args.precision == "bf16x3" else pk.PREC_BF16
+            prec = {"bf16": pk.PREC_BF16, "bf16x3": pk.PREC_BF16X3, "fp16": pk.PREC_FP16}[args.precision]
             a = pk.AcousticModel(c, prec).from_layers(
                 make_layers(cfg), np.full(cfg["pdfs"], 1.0 / cfg["pdfs"], np.float32), 5, 5)
         cb = pk.Batch(c, [SAMPLES_10S] * chunk, g, a, prob_scale=0.1)
@@ -409,15 +427,28 @@ def run_e2e(args, cfg, ctx, am, g, rank, local, dist, n_utts):
                    "buffers, two contexts alternating so D2H overlaps the next chunk"}
 
 
-def parity_sample(cfg, batch, layers, prior, g):
-    """GPU output of utterance 0 against the unmodified reference on the same PCM (checker only)."""
-    import pocketkaldi_b200 as pk
+def reference_outputs(cfg, g):
+    """The unmodified reference on utterance 0 of the synthetic corpus (checker only)."""
     from oracle.oracle import Reference
     from pocketkaldi_b200.synth import synth_pcm
     ref = Reference()
     pcm = synth_pcm(1234, [0], SAMPLES_10S)[0].astype(np.float32)
     raw = ref.fbank(pcm)
     feats = ref.cmvn(raw, g)
+    ll = None
+    if cfg["nnet"]:
+        with tempfile.TemporaryDirectory(prefix="pkb_parity_") as tmp:
+            conf, _, _ = write_reference_model(cfg, tmp)
+            am = ref.am_load(conf)
+            ll = ref.am_compute(am, feats) * np.float32(0.1)
+            ref.am_free(am)
+    return raw, feats, ll
+
+
+def parity_sample(cfg, batch, ref_pack):
+    """GPU output of utterance 0 (first rows of the batch) against reference_outputs()."""
+    import pocketkaldi_b200 as pk
+    raw, feats, ll_ref = ref_pack
     out = {"frames": int(raw.shape[0])}
     got_raw = np.empty((FRAMES_10S, 40), np.float32)
     batch.get_rows_async(pk.BUF_RAW, 0, FRAMES_10S, got_raw)
@@ -426,17 +457,40 @@ def parity_sample(cfg, batch, layers, prior, g):
     batch.ctx.sync()
     out["fbank_max_rel_err"] = float(np.max(np.abs(got_raw - raw) / np.abs(raw)))
     out["cmvn_max_err_rel_to_max1"] = float(np.max(np.abs(got_ft - feats) / np.maximum(1.0, np.abs(feats))))
-    if cfg["nnet"]:
-        with tempfile.TemporaryDirectory(prefix="pkb_parity_") as tmp:
-            conf, _, _ = write_reference_model(cfg, tmp)
-            am = ref.am_load(conf)
-            ll_ref = ref.am_compute(am, feats) * np.float32(0.1)
-            ref.am_free(am)
+    if ll_ref is not None:
         got = np.empty((FRAMES_10S, cfg["pdfs"]), np.float32)
         batch.get_rows_async(pk.BUF_LOGLIK, 0, FRAMES_10S, got)
         batch.ctx.sync()
         out["loglik_max_abs_err_unscaled"] = float(np.max(np.abs(got - ll_ref)) / 0.1)
         out["argmax_agreement"] = float(np.mean(got.argmax(1) == ll_ref.argmax(1)))
+        out["tolerance"] = "north_star: |dLL| <= 2e-2, argmax agreement >= 0.999"
+    return out
+
+
+def measure_other_modes(args, cfg, ctx, g, ref_pack, skip):
+    """Throughput + parity of the other GEMM precisions on a 512-utterance batch (same net)."""
+    import pocketkaldi_b200 as pk
+    modes = {"bf16": pk.PREC_BF16, "fp16": pk.PREC_FP16, "bf16x3": pk.PREC_BF16X3}
+    out = {}
+    layers = make_layers(cfg)
+    prior = np.full(cfg["pdfs"], 1.0 / cfg["pdfs"], np.float32)
+    for name, prec in modes.items():
+        if name == skip:
+            continue
+        am = pk.AcousticModel(ctx, prec).from_layers(layers, prior, 5, 5)
+        b = pk.Batch(ctx, [SAMPLES_10S] * 512, g, am, prob_scale=0.1)
+        b.synth_pcm(1234, 0)
+        for _ in range(2):
+            b.run(pk.STAGE_ALL)
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(3):
+            b.run(pk.STAGE_ALL)
+        ms = ctx.timer_stop()
+        out[name] = {"value": b.total_frames * 3 / (ms * 1e-3), "unit": "frames/s",
+                     "utts": 512, "parity": parity_sample(cfg, b, ref_pack)}
+        b.close()
+        am.close()
     return out
 
 
@@ -449,7 +503,7 @@ def run_stream_arm(args, cfg):
     rank, world, local, dist = dist_setup(args.gpus)
     ctx = pk.Context(local)
     g = synth_global_cmvn()
-    prec = pk.PREC_BF16X3 if args.precision == "bf16x3" else pk.PREC_BF16
+    prec = {"bf16": pk.PREC_BF16, "bf16x3": pk.PREC_BF16X3, "fp16": pk.PREC_FP16}[args.precision]
     S, chunk = args.utts or cfg["utts"], 2560
     layers = make_layers(cfg)
     prior = np.full(cfg["pdfs"], 1.0 / cfg["pdfs"], np.float32)
@@ -487,7 +541,7 @@ def run_stream_arm(args, cfg):
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if prec == pk.PREC_BF16 else "bf16x3", "data": "synthetic",
+            "dtype": args.precision, "data": "synthetic",
             "config": {"workload": cfg["name"], "streams_per_gpu": S, "chunk_samples": chunk,
                        "timing": "host wall clock around the synchronous push (H2D + kernels + D2H)"},
             "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
@@ -514,7 +568,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="3", choices=sorted(CONFIGS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp16"])
     ap.add_argument("--utts", type=int, default=0, help="utterances per GPU (default: the config's)")
     ap.add_argument("--e2e-chunk", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=2)

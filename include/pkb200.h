@@ -34,6 +34,8 @@ extern "C" {
 /* ---- GEMM arithmetic of the nnet (src/gemm.cc, src/gemm_haswell.cc) ------- */
 #define PKB_PREC_BF16 0   /* one BF16 tcgen05 MMA per product, FP32 accumulate      */
 #define PKB_PREC_BF16X3 1 /* split BF16 (hi+lo), 3 MMAs: FP32-class accuracy; parity mode */
+#define PKB_PREC_FP16 2   /* one FP16 MMA per product (11-bit significand, BF16 speed); operands
+                             must stay below 65504 in magnitude                              */
 
 /* ---- fixed front-end geometry (src/fbank.h:7-13, src/cmvn.h:10-11) -------- */
 #define PKB_FBANK_DIM 40

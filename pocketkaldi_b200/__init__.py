@@ -24,6 +24,7 @@ from .binding import (  # noqa: F401
     load_library,
     PREC_BF16,
     PREC_BF16X3,
+    PREC_FP16,
     STAGE_FBANK,
     STAGE_CMVN,
     STAGE_NNET,

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpkb200.so")
 CSRC = os.path.join(HERE, "csrc")
 
-PREC_BF16, PREC_BF16X3 = 0, 1
+PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2
 STAGE_FBANK, STAGE_CMVN, STAGE_NNET, STAGE_ALL = 1, 2, 4, 7
 BUF_PCM, BUF_RAW, BUF_FEATS, BUF_LOGLIK = 0, 1, 2, 3
 KERNEL_CLASSES = ("fbank", "cmvn", "gemm", "gemm_final", "misc")

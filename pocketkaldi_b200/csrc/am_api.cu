@@ -351,7 +351,7 @@ int pkb_am_compute(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t
   __nv_bfloat16 *hi = ws.feat_hi.as<__nv_bfloat16>();
   __nv_bfloat16 *lo = am->planes == 2 ? ws.feat_lo.as<__nv_bfloat16>() : nullptr;
   PKB_TRY(pkb::launch_pack_padded(c, am->in_f32.as<float>(), m, feat_dim, dp, am->left, am->right,
-                                  ws.pad_off.as<int64_t>(), hi, lo, ws.row_map.as<int32_t>()));
+                                  ws.pad_off.as<int64_t>(), hi, lo, ws.row_map.as<int32_t>(), am->fp16));
   InputView in;
   in.hi = hi;
   in.lo = lo;
@@ -389,7 +389,7 @@ int pkb_nnet_propagate(pkb_ctx_t *c, pkb_am_t *am, const float *in_host, int row
   PKB_CUDA(cudaMemcpyAsync(am->in_f32.p, in_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
   __nv_bfloat16 *hi = ws.feat_hi.as<__nv_bfloat16>();
   __nv_bfloat16 *lo = am->planes == 2 ? ws.feat_lo.as<__nv_bfloat16>() : nullptr;
-  PKB_TRY(pkb::launch_pack_plain(c, am->in_f32.as<float>(), rows, in_dim, dp, hi, lo));
+  PKB_TRY(pkb::launch_pack_plain(c, am->in_f32.as<float>(), rows, in_dim, dp, hi, lo, am->fp16));
   InputView in;
   in.hi = hi;
   in.lo = lo;
@@ -462,6 +462,7 @@ int pkb_batch_create(pkb_ctx_t *c, pkb_am_t *am, int n_utts, const int32_t *num_
       b->planes.left = am->left;
       b->planes.right = am->right;
       b->planes.dim_pad = dp;
+      b->planes.fp16 = am->fp16;
     }
     if ((rc = pkb::prepare_cmvn_tables(c, global_stats)) != PKB_OK) break;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {

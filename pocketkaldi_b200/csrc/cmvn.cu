@@ -31,7 +31,7 @@ cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off
             const float *__restrict__ tab /* alpha[600], scale[600], global[41] */,
             float *__restrict__ out, __nv_bfloat16 *__restrict__ p_hi,
             __nv_bfloat16 *__restrict__ p_lo, const int64_t *__restrict__ pad_off, int left,
-            int right, int dim_pad) {
+            int right, int dim_pad, int fp16) {
   __shared__ float s_alpha[kCmvnWindow];
   __shared__ float s_scale[kCmvnWindow];
   for (int i = threadIdx.x; i < kCmvnWindow; i += blockDim.x) {
@@ -73,8 +73,8 @@ cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off
         const float v = __fadd_rn(xv[i], __fmul_rn(-s_scale[ti], s));
         if (y) y[static_cast<int64_t>(t) * kMel] = v;
         if (ph) {
-          const __nv_bfloat16 h = __float2bfloat16_rn(v);
-          const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+          const __nv_bfloat16 h = operand_bits(v, fp16);
+          const __nv_bfloat16 l = operand_bits(v - operand_value(h, fp16), fp16);
           const int64_t row = left + t;
           ph[row * dim_pad] = h;
           if (pl) pl[row * dim_pad] = l;
@@ -184,7 +184,7 @@ int launch_cmvn(Ctx *c, const float *d_raw, const BatchMeta &m, float *d_out,
       d_raw, m.d_frame_off, m.d_num_frames, m.n_utts, c->cmvn_tab.as<float>(), d_out,
       planes ? planes->hi : nullptr, planes ? planes->lo : nullptr,
       planes ? planes->d_pad_off : nullptr, planes ? planes->left : 0,
-      planes ? planes->right : 0, planes ? planes->dim_pad : 0);
+      planes ? planes->right : 0, planes ? planes->dim_pad : 0, planes ? planes->fp16 : 0);
   PKB_CUDA(cudaGetLastError());
   return PKB_OK;
 }

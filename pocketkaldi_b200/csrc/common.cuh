@@ -3,8 +3,10 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -134,7 +136,28 @@ struct PaddedPlanes {
   __nv_bfloat16 *lo = nullptr;  // nullptr in PKB_PREC_BF16
   const int64_t *d_pad_off = nullptr;  // [n_utts] first padded row of each utterance
   int left = 0, right = 0, dim_pad = 0;
+  int fp16 = 0;  // planes hold FP16 bit patterns instead of BF16 (PKB_PREC_FP16)
 };
+
+// 16-bit GEMM operand encoding of v: BF16 (default) or FP16 bits, stored in __nv_bfloat16 slots.
+__host__ __device__ inline __nv_bfloat16 operand_bits(float v, int fp16) {
+  if (fp16) {
+    const __half_raw hr = static_cast<__half_raw>(__float2half_rn(v));
+    __nv_bfloat16_raw br;
+    br.x = hr.x;
+    return __nv_bfloat16(br);
+  }
+  return __float2bfloat16_rn(v);
+}
+__host__ __device__ inline float operand_value(__nv_bfloat16 b, int fp16) {
+  if (fp16) {
+    const __nv_bfloat16_raw br = static_cast<__nv_bfloat16_raw>(b);
+    __half_raw hr;
+    hr.x = br.x;
+    return __half2float(__half(hr));
+  }
+  return __bfloat162float(b);
+}
 int prepare_cmvn_tables(Ctx *c, const float *global_stats);
 int launch_cmvn(Ctx *c, const float *d_raw, const BatchMeta &m, float *d_out,
                 const PaddedPlanes *planes);

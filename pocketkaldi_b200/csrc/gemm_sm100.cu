@@ -190,8 +190,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 
 // cute::UMMA::InstrDescriptor for kind::f16: D=F32 (1<<4), A=B=BF16 (1<<7, 1<<10),
 // both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+// fmt: 1 = BF16, 0 = F16 for both operands.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
@@ -233,6 +234,10 @@ __device__ __forceinline__ float exp2f_fast(float x) {
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
@@ -349,7 +354,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBlockM, BN);
+      const uint32_t idesc = make_idesc(kBlockM, BN, p.fp16 ? 0u : 1u);
       uint32_t s = 0, ph = 0;
       int m_blk, n_blk;
       for (int it = 0; get_tile(p, it, m_blk, n_blk); ++it) {
@@ -463,7 +468,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             }
             uint32_t hi[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) hi[i] = pack_bf16(z[2 * i], z[2 * i + 1]);
+            for (int i = 0; i < 16; ++i)
+              hi[i] = p.fp16 ? pack_f16(z[2 * i], z[2 * i + 1]) : pack_bf16(z[2 * i], z[2 * i + 1]);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               st_shared_v4(stg_w + (((h * 4 + j) ^ (lane & 7)) << 4), hi[4 * j], hi[4 * j + 1],

@@ -44,6 +44,7 @@ struct GemmParams {
   float in_dim;        // D of the NormalizeLayer feeding this stage
   float *out_sumsq;    // [M][n_tiles_n] or nullptr
   int relu;
+  int fp16;            // operands (and hidden outputs) are FP16 instead of BF16
   __nv_bfloat16 *out_hi, *out_lo;  // [M][ld_out]
   int ld_out;
   float *out_f32;      // final: [M][ld_f32], GEMM row m -> output row m (padded-row layout)

@@ -26,7 +26,7 @@ __global__ void pack_padded_kernel(const float *__restrict__ feats,
                                    const int64_t *__restrict__ pad_off, int n_utts, int dim,
                                    int dim_pad, int left, int right, int64_t total_frames,
                                    __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
-                                   int32_t *__restrict__ row_map) {
+                                   int32_t *__restrict__ row_map, int fp16) {
   // one thread per (frame, padded column)
   const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t f = g / dim_pad;
@@ -41,8 +41,8 @@ __global__ void pack_padded_kernel(const float *__restrict__ feats,
   const int t = static_cast<int>(f - frame_off[u]);
   const int T = num_frames[u];
   const float v = d < dim ? feats[f * dim + d] : 0.0f;
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  const __nv_bfloat16 h = operand_bits(v, fp16);
+  const __nv_bfloat16 l = operand_bits(v - operand_value(h, fp16), fp16);
   const int64_t base = pad_off[u];
   const int64_t row = base + left + t;
   hi[row * dim_pad + d] = h;
@@ -73,15 +73,16 @@ __global__ void row_map_kernel(const int64_t *__restrict__ frame_off,
 }
 
 __global__ void pack_plain_kernel(const float *__restrict__ in, int64_t rows, int dim, int dim_pad,
-                                  __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+                                  __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
+                                  int fp16) {
   const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t r = g / dim_pad;
   const int d = static_cast<int>(g % dim_pad);
   if (r >= rows) return;
   const float v = d < dim ? in[r * dim + d] : 0.0f;
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 h = operand_bits(v, fp16);
   hi[g] = h;
-  if (lo) lo[g] = __float2bfloat16_rn(v - __bfloat162float(h));
+  if (lo) lo[g] = operand_bits(v - operand_value(h, fp16), fp16);
 }
 
 __global__ void scale_kernel(float *x, int64_t n, float s) {
@@ -94,7 +95,7 @@ __global__ void scale_kernel(float *x, int64_t n, float s) {
 // W[out][in] float -> BF16 planes [n_pad][k_pad]; column c of the source goes to
 // column remap(c) (identity, or the padded splice layout).
 int pack_stage(Ctx *c, Stage *st, const float *W, const float *b, int out_dim, int in_dim,
-               int group, int group_pad, int planes) {
+               int group, int group_pad, int planes, int fp16) {
   st->in_dim = in_dim;
   st->out_dim = out_dim;
   const int groups = group > 0 ? in_dim / group : 1;
@@ -105,17 +106,17 @@ int pack_stage(Ctx *c, Stage *st, const float *W, const float *b, int out_dim, i
   st->block_n = (n256 * 100 <= n128 * 106) ? 256 : 128;
   st->n_pad = st->block_n == 256 ? n256 : n128;
   const size_t elems = static_cast<size_t>(st->n_pad) * st->k_pad;
-  std::vector<__nv_bfloat16> hi(elems, __float2bfloat16_rn(0.0f)), lo;
-  if (planes == 2) lo.assign(elems, __float2bfloat16_rn(0.0f));
+  std::vector<__nv_bfloat16> hi(elems, operand_bits(0.0f, fp16)), lo;
+  if (planes == 2) lo.assign(elems, operand_bits(0.0f, fp16));
   for (int o = 0; o < out_dim; ++o) {
     const float *src = W + static_cast<size_t>(o) * in_dim;
     __nv_bfloat16 *dh = hi.data() + static_cast<size_t>(o) * st->k_pad;
     __nv_bfloat16 *dl = planes == 2 ? lo.data() + static_cast<size_t>(o) * st->k_pad : nullptr;
     for (int k = 0; k < in_dim; ++k) {
       const int kk = group > 0 ? (k / group) * group_pad + (k % group) : k;
-      const __nv_bfloat16 h = __float2bfloat16_rn(src[k]);
+      const __nv_bfloat16 h = operand_bits(src[k], fp16);
       dh[kk] = h;
-      if (dl) dl[kk] = __float2bfloat16_rn(src[k] - __bfloat162float(h));
+      if (dl) dl[kk] = operand_bits(src[k] - operand_value(h, fp16), fp16);
     }
   }
   std::vector<float> bias(st->n_pad, 0.0f);
@@ -169,7 +170,7 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
              const float *prior, int num_pdfs, int left, int right, const int32_t *tid2pdf,
              int n_tid2pdf, int precision, pkb_am **out) {
   PKB_REQUIRE(c && out, "pkb_am_create: NULL argument");
-  PKB_REQUIRE(precision == PKB_PREC_BF16 || precision == PKB_PREC_BF16X3,
+  PKB_REQUIRE(precision == PKB_PREC_BF16 || precision == PKB_PREC_BF16X3 || precision == PKB_PREC_FP16,
               "pkb_am_create: unknown precision %d", precision);
   PKB_REQUIRE(left >= 0 && right >= 0, "pkb_am_create: negative context");
   PKB_REQUIRE(n_layers > 0 && types, "pkb_am_create: empty layer list");
@@ -178,6 +179,7 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
   am->c = c;
   am->precision = precision;
   am->planes = precision == PKB_PREC_BF16X3 ? 2 : 1;
+  am->fp16 = precision == PKB_PREC_FP16 ? 1 : 0;
   am->left = left;
   am->right = right;
   int rc = PKB_OK;
@@ -204,7 +206,7 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
     }
     am->stages.emplace_back();
     Stage &st = am->stages.back();
-    rc = pack_stage(c, &st, weights[lin], biases[lin], od, id, 0, 0, am->planes);
+    rc = pack_stage(c, &st, weights[lin], biases[lin], od, id, 0, 0, am->planes, am->fp16);
     if (rc != PKB_OK) break;
     if (lin == 0) {
       am->input_dim = id;
@@ -260,7 +262,7 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
       am->feat_dim_pad = round_up(am->feat_dim, 8);  // 16-byte row pitch for the TMA view
       rc = pack_stage(c, &am->splice_stage, am->w0_host.data(), am->b0_host.data(),
                       am->stages[0].out_dim, am->input_dim, am->feat_dim, am->feat_dim_pad,
-                      am->planes);
+                      am->planes, am->fp16);
       if (rc == PKB_OK) {
         am->splice_stage.relu = am->stages[0].relu;
         am->splice_stage.normalize = am->stages[0].normalize;
@@ -338,6 +340,7 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
     p.in_sumsq_tiles = in_sumsq_tiles;
     p.in_dim = in_dim;
     p.relu = st.relu ? 1 : 0;
+    p.fp16 = am->fp16;
     if (!final) {
       const int buf = static_cast<int>(i & 1);
       p.out_hi = ws->act_hi[buf].as<__nv_bfloat16>();
@@ -433,25 +436,25 @@ int launch_checksum_rows(Ctx *c, const float *d, int cols, int64_t rows, const i
 
 int launch_pack_padded(Ctx *c, const float *d_feats, const BatchMeta &m, int dim, int dim_pad,
                        int left, int right, const int64_t *d_pad_off, __nv_bfloat16 *hi,
-                       __nv_bfloat16 *lo, int32_t *row_map) {
+                       __nv_bfloat16 *lo, int32_t *row_map, int fp16) {
   if (m.total_frames == 0) return PKB_OK;
   const int64_t threads = m.total_frames * dim_pad;
   const int grid = static_cast<int>((threads + 255) / 256);
   LaunchScope scope(c, PKB_KERNEL_MISC);
   pack_padded_kernel<<<grid, 256, 0, c->stream>>>(d_feats, m.d_frame_off, m.d_num_frames, d_pad_off,
                                                   m.n_utts, dim, dim_pad, left, right,
-                                                  m.total_frames, hi, lo, row_map);
+                                                  m.total_frames, hi, lo, row_map, fp16);
   PKB_CUDA(cudaGetLastError());
   return PKB_OK;
 }
 
 int launch_pack_plain(Ctx *c, const float *d_in, int64_t rows, int dim, int dim_pad,
-                      __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
+                      __nv_bfloat16 *hi, __nv_bfloat16 *lo, int fp16) {
   if (rows == 0) return PKB_OK;
   const int64_t threads = rows * dim_pad;
   const int grid = static_cast<int>((threads + 255) / 256);
   LaunchScope scope(c, PKB_KERNEL_MISC);
-  pack_plain_kernel<<<grid, 256, 0, c->stream>>>(d_in, rows, dim, dim_pad, hi, lo);
+  pack_plain_kernel<<<grid, 256, 0, c->stream>>>(d_in, rows, dim, dim_pad, hi, lo, fp16);
   PKB_CUDA(cudaGetLastError());
   return PKB_OK;
 }

@@ -51,6 +51,7 @@ struct pkb_am {
   pkb::Ctx *c = nullptr;
   int precision = PKB_PREC_BF16;
   int planes = 1;
+  int fp16 = 0;  // operands are FP16 instead of BF16 (PKB_PREC_FP16)
   int left = 0, right = 0, num_pdfs = 0;
   int input_dim = 0;   // nnet input dim
   int feat_dim = 0;    // input_dim / (left + right + 1) when divisible, else 0
@@ -100,10 +101,10 @@ int launch_checksum_rows(Ctx *c, const float *d, int cols, int64_t rows, const i
 // float [F][dim] -> padded BF16 planes with replicated edge frames + row map.
 int launch_pack_padded(Ctx *c, const float *d_feats, const BatchMeta &m, int dim, int dim_pad,
                        int left, int right, const int64_t *d_pad_off, __nv_bfloat16 *hi,
-                       __nv_bfloat16 *lo, int32_t *row_map);
+                       __nv_bfloat16 *lo, int32_t *row_map, int fp16);
 // float [rows][dim] -> BF16 planes [rows][dim_pad] (zero padded columns).
 int launch_pack_plain(Ctx *c, const float *d_in, int64_t rows, int dim, int dim_pad,
-                      __nv_bfloat16 *hi, __nv_bfloat16 *lo);
+                      __nv_bfloat16 *hi, __nv_bfloat16 *lo, int fp16);
 // row_map for a padded batch without packing (the CMVN kernel wrote the planes).
 int launch_row_map(Ctx *c, const BatchMeta &m, int left, int right, const int64_t *d_pad_off,
                    int32_t *row_map, int64_t rows);

@@ -55,7 +55,8 @@ __global__ void cmvn_stream_kernel(const float *__restrict__ raw /* [S][n_new][4
                                    int64_t t0, const float *__restrict__ tab, float *__restrict__ stat,
                                    float *__restrict__ ring /* [S][600][40] */,
                                    __nv_bfloat16 *__restrict__ p_hi, __nv_bfloat16 *__restrict__ p_lo,
-                                   int win_rows, int carry, int left, int dim_pad, int n_streams) {
+                                   int win_rows, int carry, int left, int dim_pad, int n_streams,
+                                   int fp16) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = g / kMel, d = g % kMel;
   if (s >= n_streams) return;
@@ -76,8 +77,8 @@ __global__ void cmvn_stream_kernel(const float *__restrict__ raw /* [S][n_new][4
     float sm = st;
     if (t < kCmvnWindow - 1) sm = __fadd_rn(sm, __fmul_rn(tab[ti], gd));
     const float v = __fadd_rn(x, __fmul_rn(-tab[kCmvnWindow + ti], sm));
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const __nv_bfloat16 h = operand_bits(v, fp16);
+    const __nv_bfloat16 l = operand_bits(v - operand_value(h, fp16), fp16);
     const size_t row = static_cast<size_t>(carry + k) * dim_pad;
     ph[row] = h;
     if (pl) pl[row] = l;
@@ -271,7 +272,7 @@ int pkb_stream_push_i16(pkb_stream_t *st, const int16_t *pcm, float *loglik_out,
       const int threads = S * pkb::kMel;
       pkb::cmvn_stream_kernel<<<(threads + 127) / 128, 128, 0, c->stream>>>(
           st->raw.as<float>(), n_new, st->n_feat, c->cmvn_tab.as<float>(), st->stat.as<float>(),
-          st->ring.as<float>(), hi, lo, rows, carry, st->L, st->Dp, S);
+          st->ring.as<float>(), hi, lo, rows, carry, st->L, st->Dp, S, am->fp16);
       PKB_CUDA(cudaGetLastError());
     }
     st->n_feat += n_new;

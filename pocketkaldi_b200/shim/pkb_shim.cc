@@ -26,10 +26,11 @@ pkb_ctx_t *shim_ctx() {
   return ctx;
 }
 
-// GEMM arithmetic from PKB_PRECISION: "bf16" or "bf16x3" (default: the parity mode).
+// GEMM arithmetic from PKB_PRECISION: "bf16", "fp16" or "bf16x3" (default: the parity mode).
 int shim_precision() {
   const char *p = getenv("PKB_PRECISION");
   if (p != nullptr && strcmp(p, "bf16") == 0) return PKB_PREC_BF16;
+  if (p != nullptr && strcmp(p, "fp16") == 0) return PKB_PREC_FP16;
   return PKB_PREC_BF16X3;
 }
 

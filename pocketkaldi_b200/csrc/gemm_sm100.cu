@@ -118,18 +118,70 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster share one 256-row MMA tile. In a cluster
+// launch bit 24 of a shared-window address selects the CTA of the pair; clearing it addresses
+// the same offset in the leader (even) CTA (cute::Sm100MmaPeerBitMask).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// both CTAs of a pair load their part of a stage and signal the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *bar,
+                                                 int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c_inner),
+      "r"(c_outer)
+      : "memory");
+}
+
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                   smem_u32(dst)),
-               "r"(ncols)
-               : "memory");
+  if (CG == 1)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(dst)),
+                 "r"(ncols)
+                 : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(dst)),
+                 "r"(ncols)
+                 : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (CG == 1)
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  else
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
-               : "memory");
+  if (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -139,23 +191,45 @@ __device__ __forceinline__ void tc_fence_after() {
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, BF16 inputs, FP32 accumulate.
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (CG == 1)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 
-// Arrives on `bar` once all previously issued tcgen05.mma of this thread finished.
+// Arrives on `bar` once all previously issued tcgen05.mma of this thread finished; for a CTA
+// pair the arrival is multicast to the barrier at the same offset in both CTAs.
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;" ::"r"(smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+  }
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -245,10 +319,10 @@ struct SmemLayout {
   uint32_t stage_bytes, a_plane, w_plane, stages, epi_off, epi_bytes, bar_off, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool final) {
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool final, int cg) {
   SmemLayout L;
   L.a_plane = kBlockM * kBlockK * 2;
-  L.w_plane = block_n * kBlockK * 2;
+  L.w_plane = (block_n / cg) * kBlockK * 2;  // a CTA pair splits the W tile
   L.stage_bytes = planes * (L.a_plane + L.w_plane);
   // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
   // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch
@@ -267,27 +341,36 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool 
 // softmax stage): the grid is a whole number of groups of n_tiles_n CTAs; a group owns one
 // row block per iteration and each of its CTAs always owns the same column tile, so the CTAs
 // that exchange softmax partials are a fixed team working on the same iteration.
-__device__ __forceinline__ bool get_tile(const GemmParams &p, int it, int &m_blk, int &n_blk) {
+// With CTA pairs (CG == 2) the unit of scheduling is the cluster: it owns a pair of
+// consecutive row blocks, CTA `rank` of the pair taking row block 2*pair + rank (which may lie
+// past the end of the matrix for an odd block count; such a CTA computes on zero rows).
+template <int CG>
+__device__ __forceinline__ bool get_tile(const GemmParams &p, int it, uint32_t rank, int &m_blk,
+                                         int &n_blk) {
+  const int unit = static_cast<int>(blockIdx.x) / CG;
+  const int n_units = static_cast<int>(gridDim.x) / CG;
+  const int m_units = (p.m_tiles + CG - 1) / CG;
+  int mu;
   if (p.group_sched) {
-    const int groups = gridDim.x / p.n_tiles_n;
-    m_blk = static_cast<int>(blockIdx.x) / p.n_tiles_n + it * groups;
-    n_blk = static_cast<int>(blockIdx.x) % p.n_tiles_n;
-    return m_blk < p.m_tiles;
+    const int groups = n_units / p.n_tiles_n;
+    mu = unit / p.n_tiles_n + it * groups;
+    n_blk = unit % p.n_tiles_n;
+  } else {
+    const int tile = unit + it * n_units;
+    mu = tile / p.n_tiles_n;
+    n_blk = tile % p.n_tiles_n;
   }
-  const int tile = blockIdx.x + it * gridDim.x;
-  if (tile >= p.num_tiles) return false;
-  m_blk = tile / p.n_tiles_n;
-  n_blk = tile % p.n_tiles_n;
-  return true;
+  m_blk = mu * CG + static_cast<int>(rank);
+  return mu < m_units;
 }
 
-template <int BN, int PLANES, bool FINAL>
+template <int BN, int PLANES, bool FINAL, int CG>
 __global__ void __launch_bounds__(num_threads(FINAL), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
             const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const SmemLayout L = smem_layout(BN, PLANES, FINAL);
+  const SmemLayout L = smem_layout(BN, PLANES, FINAL, CG);
   uint8_t *smem = reinterpret_cast<uint8_t *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
@@ -299,6 +382,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t S = L.stages;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     if (FINAL) tma_prefetch_desc(&tm_out);
@@ -316,16 +401,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], epi_warps(FINAL));
+      mbar_init(&tempty[i], CG * epi_warps(FINAL));  // both CTAs of a pair release the leader
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 2 * BN);
-    tmem_relinquish();
+    tmem_alloc<CG>(tmem_slot, 2 * BN);
+    tmem_relinquish<CG>();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // peers' barriers are initialised too
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -334,18 +419,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       int m_blk, n_blk;
-      for (int it = 0; get_tile(p, it, m_blk, n_blk); ++it) {
+      for (int it = 0; get_tile<CG>(p, it, cta_rank, m_blk, n_blk); ++it) {
         const int m0 = m_blk * kBlockM;
-        const int n0 = n_blk * BN;
+        const int n0 = n_blk * BN + static_cast<int>(cta_rank) * (BN / CG);  // this CTA's W rows
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait<64>(&empty[s], ph ^ 1);
           uint8_t *st = smem + s * L.stage_bytes;
-          mbar_expect_tx(&full[s], L.stage_bytes);
-          tma_load_2d(st, &tm_a_hi, &full[s], kb * kBlockK, m0);
-          tma_load_2d(st + PLANES * L.a_plane, &tm_w_hi, &full[s], kb * kBlockK, n0);
-          if (PLANES == 2) {
-            tma_load_2d(st + L.a_plane, &tm_a_lo, &full[s], kb * kBlockK, m0);
-            tma_load_2d(st + 2 * L.a_plane + L.w_plane, &tm_w_lo, &full[s], kb * kBlockK, n0);
+          if (CG == 1) {
+            mbar_expect_tx(&full[s], L.stage_bytes);
+            tma_load_2d(st, &tm_a_hi, &full[s], kb * kBlockK, m0);
+            tma_load_2d(st + PLANES * L.a_plane, &tm_w_hi, &full[s], kb * kBlockK, n0);
+            if (PLANES == 2) {
+              tma_load_2d(st + L.a_plane, &tm_a_lo, &full[s], kb * kBlockK, m0);
+              tma_load_2d(st + 2 * L.a_plane + L.w_plane, &tm_w_lo, &full[s], kb * kBlockK, n0);
+            }
+          } else {
+            // the leader's barrier collects the bytes of both CTAs' loads
+            if (leader) mbar_expect_tx(&full[s], 2 * L.stage_bytes);
+            tma_load_2d_pair(st, &tm_a_hi, &full[s], kb * kBlockK, m0);
+            tma_load_2d_pair(st + PLANES * L.a_plane, &tm_w_hi, &full[s], kb * kBlockK, n0);
+            if (PLANES == 2) {
+              tma_load_2d_pair(st + L.a_plane, &tm_a_lo, &full[s], kb * kBlockK, m0);
+              tma_load_2d_pair(st + 2 * L.a_plane + L.w_plane, &tm_w_lo, &full[s], kb * kBlockK, n0);
+            }
           }
           if (++s == S) { s = 0; ph ^= 1; }
         }
@@ -353,11 +449,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(kBlockM, BN, p.fp16 ? 0u : 1u);
+    if (lane == 0 && leader) {  // a CTA pair's MMAs are issued by the leader alone
+      const uint32_t idesc = make_idesc(kBlockM * CG, BN, p.fp16 ? 0u : 1u);
       uint32_t s = 0, ph = 0;
       int m_blk, n_blk;
-      for (int it = 0; get_tile(p, it, m_blk, n_blk); ++it) {
+      for (int it = 0; get_tile<CG>(p, it, cta_rank, m_blk, n_blk); ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
         mbar_wait<32>(&tempty[as], aph ^ 1);
         tc_fence_after();
@@ -372,7 +468,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-            umma_bf16(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+            umma_bf16<CG>(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
           }
           if (PLANES == 2) {
             const uint64_t a_lo = make_smem_desc(sa + L.a_plane);
@@ -380,14 +476,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-              umma_bf16(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
-              umma_bf16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+              umma_bf16<CG>(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
+              umma_bf16<CG>(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
             }
           }
-          umma_commit(&empty[s]);  // frees the smem stage once these MMAs retire
+          umma_commit<CG>(&empty[s]);  // frees the smem stage (in both CTAs) once these MMAs retire
           if (++s == S) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[as]);  // accumulator complete
+        umma_commit<CG>(&tfull[as]);  // accumulator complete
       }
     }
   } else if (warp >= 4) {
@@ -405,7 +501,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     float *s_lp = s_bias + BN;
     constexpr int kEpiThreads = 32 * epi_warps(FINAL);
     if (FINAL && p.group_sched) {
-      const int nb = static_cast<int>(blockIdx.x) % p.n_tiles_n;
+      const int nb = (static_cast<int>(blockIdx.x) / CG) % p.n_tiles_n;
       for (int i = threadIdx.x - kMainThreads; i < BN; i += kEpiThreads) {
         s_bias[i] = p.bias[nb * BN + i];
         s_lp[i] = p.log_prior[nb * BN + i];
@@ -415,7 +511,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     const int t_row = lane >> 3, t_chunk = lane & 7;            // transposed read role
     uint32_t store_seq = 0;  // staging-buffer parity of this warp's TMA stores
     int m_blk, n_blk;
-    for (int it = 0; get_tile(p, it, m_blk, n_blk); ++it) {
+    for (int it = 0; get_tile<CG>(p, it, cta_rank, m_blk, n_blk); ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       const int m0 = m_blk * kBlockM;
       const int n0 = n_blk * BN;
@@ -503,7 +599,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         // all TMEM reads of this accumulator are done: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tempty[as]); else mbar_arrive_remote(&tempty[as], 0);
+        }
         if (p.out_sumsq != nullptr && row_ok)
           p.out_sumsq[static_cast<size_t>(row) * p.n_tiles_n + n_blk] = sumsq;
       } else {
@@ -645,7 +743,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tempty[as]); else mbar_arrive_remote(&tempty[as], 0);
+        }
         if (dbg_on) {
           const long long tk5 = clock64();
           long long *d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
@@ -664,10 +764,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc<CG>(tmem_base, 2 * BN);
   }
 }
 
@@ -688,27 +788,29 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, int PLANES, bool FINAL>
+template <int BN, int PLANES, bool FINAL, int CG>
 int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const CUtensorMap *w_hi,
                const CUtensorMap *w_lo, const GemmParams &p) {
   // FP32 output map of the final stage (hidden stages pass a dummy copy of the A map)
   CUtensorMap out_map = *a_hi;
   if (FINAL && (p.ld_f32 & 3) == 0)
     PKB_TRY(make_output_map(&out_map, p.out_f32, p.N_valid, p.M));
-  const SmemLayout L = smem_layout(BN, PLANES, FINAL);
-  auto kern = gemm_kernel<BN, PLANES, FINAL>;
+  const SmemLayout L = smem_layout(BN, PLANES, FINAL, CG);
+  auto kern = gemm_kernel<BN, PLANES, FINAL, CG>;
   PKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  int grid = std::min(p.num_tiles, c->sm_count);
   GemmParams pp = p;
   pp.m_tiles = (p.M + kBlockM - 1) / kBlockM;
   pp.group_sched = 0;
+  const int m_units = (pp.m_tiles + CG - 1) / CG;
+  const int max_units = c->sm_count / CG;
+  int grid = CG * static_cast<int>(std::min<int64_t>(static_cast<int64_t>(m_units) * p.n_tiles_n, max_units));
   if (FINAL && p.final_mode != 0) {
     if (p.n_tiles_n > c->sm_count) {
       set_error("launch_gemm: %d column tiles exceed the %d SMs of the device", p.n_tiles_n, c->sm_count);
       return PKB_ERR_UNSUPPORTED;
     }
     pp.group_sched = 1;
-    grid = std::min(c->sm_count / p.n_tiles_n, pp.m_tiles) * p.n_tiles_n;
+    grid = CG * std::min(max_units / p.n_tiles_n, m_units) * p.n_tiles_n;
   }
   static const bool dbg_env = getenv("PKB_GEMM_DEBUG") != nullptr;
   long long *dbg = nullptr;
@@ -727,6 +829,20 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
     void *args[] = {&m0, &m1, &m2, &m3, &out_map, &pp};
     PKB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid),
                                          dim3(num_threads(FINAL)), args, L.total, c->stream));
+  } else if (CG == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(num_threads(FINAL));
+    cfg.dynamicSmemBytes = L.total;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PKB_CUDA(cudaLaunchKernelEx(&cfg, kern, *a_hi, *a_lo, *w_hi, *w_lo, out_map, pp));
   } else {
     kern<<<grid, num_threads(FINAL), L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, out_map, pp);
   }
@@ -749,7 +865,7 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
 
 }  // namespace
 
-int gemm_max_smem_bytes(int block_n, int planes) { return smem_layout(block_n, planes, true).total; }
+int gemm_max_smem_bytes(int block_n, int planes) { return smem_layout(block_n, planes, true, 1).total; }
 
 int make_tensor_map(CUtensorMap *map, const void *base, uint64_t cols, uint64_t rows,
                     uint64_t pitch_bytes, uint32_t box_rows) {
@@ -794,13 +910,20 @@ int make_output_map(CUtensorMap *map, const float *base, uint64_t cols, uint64_t
   return PKB_OK;
 }
 
-int launch_gemm(Ctx *c, int block_n, int planes, bool final, const CUtensorMap *a_hi,
+int launch_gemm(Ctx *c, int block_n, int planes, bool final, int cta_group, const CUtensorMap *a_hi,
                 const CUtensorMap *a_lo, const CUtensorMap *w_hi, const CUtensorMap *w_lo,
                 const GemmParams &p) {
   if (p.num_tiles <= 0) return PKB_OK;
   if (planes == 1) { a_lo = a_hi; w_lo = w_hi; }
+  if (cta_group == 2) {
+    // CTA pairs: hidden stages with 256-wide tiles (the W maps must have box rows block_n / 2)
+    if (block_n == 256 && planes == 1 && !final) return launch_one<256, 1, false, 2>(c, a_hi, a_lo, w_hi, w_lo, p);
+    if (block_n == 256 && planes == 2 && !final) return launch_one<256, 2, false, 2>(c, a_hi, a_lo, w_hi, w_lo, p);
+    set_error("launch_gemm: cta_group 2 is built for hidden stages with block_n 256 only");
+    return PKB_ERR_INVALID;
+  }
 #define PKB_GEMM_CASE(BN, PL, FN) \
-  if (block_n == BN && planes == PL && final == FN) return launch_one<BN, PL, FN>(c, a_hi, a_lo, w_hi, w_lo, p);
+  if (block_n == BN && planes == PL && final == FN) return launch_one<BN, PL, FN, 1>(c, a_hi, a_lo, w_hi, w_lo, p);
   PKB_GEMM_CASE(128, 1, false)
   PKB_GEMM_CASE(128, 1, true)
   PKB_GEMM_CASE(128, 2, false)

@@ -65,7 +65,9 @@ int make_tensor_map(CUtensorMap *map, const void *base, uint64_t cols, uint64_t 
                     uint64_t pitch_bytes, uint32_t box_rows);
 
 // block_n in {128, 256}; planes in {1 (BF16), 2 (BF16X3)}; final: FP32 output mode.
-int launch_gemm(Ctx *c, int block_n, int planes, bool final, const CUtensorMap *a_hi,
+// cta_group 2 (hidden stages, block_n 256): clusters of two CTAs share one 256-row tcgen05 tile,
+// each loading half of the W tile (w maps with box rows block_n / 2).
+int launch_gemm(Ctx *c, int block_n, int planes, bool final, int cta_group, const CUtensorMap *a_hi,
                 const CUtensorMap *a_lo, const CUtensorMap *w_hi, const CUtensorMap *w_lo,
                 const GemmParams &p);
 

@@ -7,6 +7,7 @@
 // decodable's prob_scale (src/decodable.cc:15).
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -136,6 +137,13 @@ int pack_stage(Ctx *c, Stage *st, const float *W, const float *b, int out_dim, i
                             static_cast<uint64_t>(st->k_pad) * 2, st->block_n));
   else
     st->tm_w_lo = st->tm_w_hi;
+  PKB_TRY(make_tensor_map(&st->tm_w_hi_half, st->w_hi.p, st->k_pad, st->n_pad,
+                          static_cast<uint64_t>(st->k_pad) * 2, st->block_n / 2));
+  if (planes == 2)
+    PKB_TRY(make_tensor_map(&st->tm_w_lo_half, st->w_lo.p, st->k_pad, st->n_pad,
+                            static_cast<uint64_t>(st->k_pad) * 2, st->block_n / 2));
+  else
+    st->tm_w_lo_half = st->tm_w_hi_half;
   (void)c;
   return PKB_OK;
 }
@@ -358,8 +366,12 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       p.scale = prob_scale;
       p.log_floor = static_cast<float>(log(static_cast<double>(static_cast<float>(1.0e-20))));
     }
-    PKB_TRY(launch_gemm(c, st.block_n, am->planes, final, &tm_a_hi, &tm_a_lo, &st.tm_w_hi,
-                        &st.tm_w_lo, p));
+    // CTA pairs for the hidden stages with 256-wide tiles and at least one full pair of row blocks
+    static const bool no_pairs = getenv("PKB_GEMM_CG1") != nullptr;
+    const int cg = (!final && st.block_n == 256 && m_tiles >= 2 && !no_pairs) ? 2 : 1;
+    PKB_TRY(launch_gemm(c, st.block_n, am->planes, final, cg, &tm_a_hi, &tm_a_lo,
+                        cg == 2 ? &st.tm_w_hi_half : &st.tm_w_hi,
+                        cg == 2 ? &st.tm_w_lo_half : &st.tm_w_lo, p));
     if (!final) {
       a_hi = p.out_hi;
       a_lo = p.out_lo;

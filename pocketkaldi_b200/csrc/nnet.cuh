@@ -18,6 +18,7 @@ struct Stage {
   bool normalize = false;       // NormalizeLayer follows  (src/nnet.cc:62-75)
   DevBuf w_hi, w_lo, bias;      // [n_pad][k_pad] BF16 planes, [n_pad] FP32
   CUtensorMap tm_w_hi, tm_w_lo;
+  CUtensorMap tm_w_hi_half, tm_w_lo_half;  // box rows block_n / 2: W halves of a CTA pair
 };
 
 // How the final stage's logits are turned into the caller's output.

@@ -31,7 +31,11 @@ namespace pkb {
 namespace {
 
 constexpr int kMainThreads = 128;   // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare
-constexpr int epi_warps(bool final) { return final ? 8 : 4; }
+// FINAL: two teams of 8 epilogue warps, team t owns TMEM accumulator stage t (every other tile),
+// so one team's softmax exchange latency is covered by the other team's work.
+constexpr int epi_teams(bool final) { return final ? 2 : 1; }
+constexpr int team_warps(bool final) { return final ? 8 : 4; }
+constexpr int epi_warps(bool final) { return epi_teams(final) * team_warps(final); }
 constexpr int num_threads(bool final) { return kMainThreads + 32 * epi_warps(final); }
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemBudget = 227 * 1024;
@@ -325,8 +329,8 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool 
   L.w_plane = (block_n / cg) * kBlockK * 2;  // a CTA pair splits the W tile
   L.stage_bytes = planes * (L.a_plane + L.w_plane);
   // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
-  // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch
-  L.epi_bytes = final ? 8 * 8192 + 2 * block_n * 4 + 128 * 8 : 4 * planes * 4096;
+  // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats)
+  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 : 4 * planes * 4096;
   uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */ - L.epi_bytes;
   L.stages = avail / L.stage_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
@@ -401,7 +405,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], CG * epi_warps(FINAL));  // both CTAs of a pair release the leader
+      mbar_init(&tempty[i], CG * team_warps(FINAL));  // both CTAs of a pair release the leader
     }
     fence_barrier_init();
   }
@@ -489,15 +493,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quadrant
-    // FINAL runs 8 epilogue warps: two per lane quadrant, each owning half of the columns
-    const int chalf = FINAL ? ((warp - 4) >> 2) : 0;
+    // FINAL: team = accumulator stage; inside a team two warps per lane quadrant, each owning
+    // half of the tile's columns
+    const int team = FINAL ? ((warp - 4) >> 3) : 0;
+    const int wt = FINAL ? ((warp - 4) & 7) : (warp - 4);
+    const int chalf = FINAL ? (wt >> 2) : 0;
+    constexpr int kTeams = epi_teams(FINAL);
+    constexpr int kTeamThreads = 32 * team_warps(FINAL);
     // per-warp staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7);
     // rows are written by their owner lane and read back 4 rows per instruction so that
     // every global store covers whole 128-byte lines
-    uint8_t *stg = smem + L.epi_off + (FINAL ? (warp - 4) * 8192 : q * (PLANES * 4096));
+    uint8_t *stg = smem + L.epi_off + (FINAL ? (warp - 4) * 4096 : q * (PLANES * 4096));
     const uint32_t stg_w = smem_u32(stg) + lane * 128;          // this lane's row
     // grouped schedule: this CTA's column tile never changes, keep its bias / log-prior in smem
-    float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + 8 * 8192);
+    float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + 16 * 4096);
     float *s_lp = s_bias + BN;
     constexpr int kEpiThreads = 32 * epi_warps(FINAL);
     if (FINAL && p.group_sched) {
@@ -506,12 +515,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         s_bias[i] = p.bias[nb * BN + i];
         s_lp[i] = p.log_prior[nb * BN + i];
       }
-      named_bar_sync(1, kEpiThreads);
+      named_bar_sync(3, kEpiThreads);
     }
     const int t_row = lane >> 3, t_chunk = lane & 7;            // transposed read role
-    uint32_t store_seq = 0;  // staging-buffer parity of this warp's TMA stores
     int m_blk, n_blk;
-    for (int it = 0; get_tile<CG>(p, it, cta_rank, m_blk, n_blk); ++it) {
+    for (int it = team; get_tile<CG>(p, it, cta_rank, m_blk, n_blk); it += kTeams) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       const int m0 = m_blk * kBlockM;
       const int n0 = n_blk * BN;
@@ -528,7 +536,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       }
 
       long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0;
-      const bool dbg_on = FINAL && p.dbg != nullptr && warp == 4 && lane == 0;
+      const bool dbg_on = FINAL && p.dbg != nullptr && warp == 4 && lane == 0;  // team 0
       if (dbg_on) tk0 = clock64();
       mbar_wait<32>(&tfull[as], aph);
       tc_fence_after();
@@ -653,11 +661,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           float2 *xbase = p.lse_part + static_cast<size_t>(m_blk) * n_parts * kBlockM;
           __stcg(&xbase[(2 * n_blk + chalf) * kBlockM + rit], make_float2(run_max, run_sum));
           if (dbg_on) tk2 = clock64();
-          named_bar_sync(1, kEpiThreads);
+          named_bar_sync(1 + team, kTeamThreads);
           // (2) one thread releases the CTA's partials device-wide (the named barrier orders the
           //     other threads' stores before it), then waits for the peer CTAs of this row block:
           //     relaxed polling, one acquire at the end
-          if (warp == 4 && lane == 0) {
+          if (wt == 0 && lane == 0) {
             red_release_add(p.tile_done + m_blk, 1);
             const long long t0 = clock64();
             while (ld_relaxed(p.tile_done + m_blk) < p.n_tiles_n) {
@@ -665,7 +673,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             }
             (void)ld_acquire(p.tile_done + m_blk);
           }
-          named_bar_sync(1, kEpiThreads);
+          named_bar_sync(1 + team, kTeamThreads);
           if (dbg_on) tk3 = clock64();
           // (3) combine the partials of this row (coalesced, independent loads)
           {
@@ -680,9 +688,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           }
         }
         if (dbg_on) tk4 = clock64();
-        // ---- pass 2: final values -> swizzled staging tile -> TMA bulk tensor store.
-        //      Two staging buffers per warp: the store of chunk c drains while chunk c+1 is
-        //      computed; the TMA unit clips rows >= M and columns >= N_valid.
+        // ---- pass 2: final values -> swizzled staging tile -> TMA bulk tensor store; the TMA
+        //      unit clips rows >= M and columns >= N_valid. One staging tile per warp: the
+        //      previous store must have read it before it is rewritten (the other team's work
+        //      fills that gap).
         const bool vec_ok = (p.ld_f32 & 3) == 0;
         const float floor_v = p.log_floor, sc = p.scale;
 #pragma unroll 1
@@ -718,22 +727,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             }
           }
           if (vec_ok) {
-            const uint32_t buf = (store_seq & 1) * 4096;
-            // the store issued two chunks ago has finished reading this buffer
-            if (lane == 0) tma_store_wait_read<1>();
+            if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              st_shared_v4(stg_w + buf + ((j ^ (lane & 7)) << 4), __float_as_uint(z[4 * j]),
+              st_shared_v4(stg_w + ((j ^ (lane & 7)) << 4), __float_as_uint(z[4 * j]),
                            __float_as_uint(z[4 * j + 1]), __float_as_uint(z[4 * j + 2]),
                            __float_as_uint(z[4 * j + 3]));
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tm_out, smem_u32(stg) + buf, col0, wrow0);
+              tma_store_2d(&tm_out, smem_u32(stg), col0, wrow0);
               tma_store_commit();
             }
-            ++store_seq;
           } else if (row_ok) {
             float *dst = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + col0;
 #pragma unroll
@@ -754,13 +760,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           d[2] += tk3 - tk2;  // publish + peer wait
           d[3] += tk4 - tk3;  // combine partials
           d[4] += tk5 - tk4;  // pass 2
-          d[5] += 1;
+          d[5] += kTeams;  // tiles of this CTA (team 0 times every other one)
         }
       }
     }
     // shared memory must stay valid until the last bulk stores have read it
     if (FINAL && lane == 0) tma_store_wait_read<0>();
-    (void)store_seq;
   }
 
   tc_fence_before();

@@ -329,8 +329,8 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool 
   L.w_plane = (block_n / cg) * kBlockK * 2;  // a CTA pair splits the W tile
   L.stage_bytes = planes * (L.a_plane + L.w_plane);
   // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
-  // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats)
-  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 : 4 * planes * 4096;
+  // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch per team
+  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 2 * 128 * 8 : 4 * planes * 4096;
   uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */ - L.epi_bytes;
   L.stages = avail / L.stage_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
@@ -654,13 +654,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             run_sum = run_sum * exp2f_fast((run_max - nm) * kLog2e) + acc;
             run_max = nm;
           }
-          // (1) publish one (max, sum) per row and column half-tile, row-fastest so that every
-          //     warp-wide access to the exchange buffer is one contiguous 256-byte segment
+          // (1) fold the two column halves of this CTA through shared memory, then publish one
+          //     (max, sum) per row and column tile, row-fastest so that every warp-wide access
+          //     to the exchange buffer is one contiguous 256-byte segment
           const int rit = q * 32 + lane;  // row inside the tile
-          const int n_parts = 2 * p.n_tiles_n;
-          float2 *xbase = p.lse_part + static_cast<size_t>(m_blk) * n_parts * kBlockM;
-          __stcg(&xbase[(2 * n_blk + chalf) * kBlockM + rit], make_float2(run_max, run_sum));
+          float2 *s_half = reinterpret_cast<float2 *>(s_lp + BN) + team * kBlockM;
+          if (chalf == 1) s_half[rit] = make_float2(run_max, run_sum);
           if (dbg_on) tk2 = clock64();
+          named_bar_sync(1 + team, kTeamThreads);
+          float2 *xbase = p.lse_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
+          if (chalf == 0) {
+            const float2 o = s_half[rit];
+            const float nm = fmaxf(run_max, o.x);
+            const float sm = run_sum * exp2f_fast((run_max - nm) * kLog2e) +
+                             o.y * exp2f_fast((o.x - nm) * kLog2e);
+            __stcg(&xbase[n_blk * kBlockM + rit], make_float2(nm, sm));
+          }
           named_bar_sync(1 + team, kTeamThreads);
           // (2) one thread releases the CTA's partials device-wide (the named barrier orders the
           //     other threads' stores before it), then waits for the peer CTAs of this row block:
@@ -678,7 +687,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           // (3) combine the partials of this row (coalesced, independent loads)
           {
             float mx = -INFINITY, ssum = 0.0f;
-            for (int j = 0; j < n_parts; ++j) {
+            for (int j = 0; j < p.n_tiles_n; ++j) {
               const float2 e = __ldcg(&xbase[j * kBlockM + rit]);
               const float nm = fmaxf(mx, e.x);
               ssum = ssum * exp2f_fast((mx - nm) * kLog2e) + e.y * exp2f_fast((e.x - nm) * kLog2e);
@@ -832,8 +841,26 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
     PKB_CUDA(cudaMemsetAsync(p.tile_done, 0, sizeof(int) * ((p.M + kBlockM - 1) / kBlockM), c->stream));
     CUtensorMap m0 = *a_hi, m1 = *a_lo, m2 = *w_hi, m3 = *w_lo;
     void *args[] = {&m0, &m1, &m2, &m3, &out_map, &pp};
-    PKB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid),
-                                         dim3(num_threads(FINAL)), args, L.total, c->stream));
+    if (CG == 1) {
+      PKB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid),
+                                           dim3(num_threads(FINAL)), args, L.total, c->stream));
+    } else {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(num_threads(FINAL));
+      cfg.dynamicSmemBytes = L.total;
+      cfg.stream = c->stream;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeCooperative;
+      attr[1].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 2;
+      PKB_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, m2, m3, out_map, pp));
+    }
   } else if (CG == 2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -924,7 +951,9 @@ int launch_gemm(Ctx *c, int block_n, int planes, bool final, int cta_group, cons
     // CTA pairs: hidden stages with 256-wide tiles (the W maps must have box rows block_n / 2)
     if (block_n == 256 && planes == 1 && !final) return launch_one<256, 1, false, 2>(c, a_hi, a_lo, w_hi, w_lo, p);
     if (block_n == 256 && planes == 2 && !final) return launch_one<256, 2, false, 2>(c, a_hi, a_lo, w_hi, w_lo, p);
-    set_error("launch_gemm: cta_group 2 is built for hidden stages with block_n 256 only");
+    if (block_n == 256 && planes == 1 && final) return launch_one<256, 1, true, 2>(c, a_hi, a_lo, w_hi, w_lo, p);
+    if (block_n == 256 && planes == 2 && final) return launch_one<256, 2, true, 2>(c, a_hi, a_lo, w_hi, w_lo, p);
+    set_error("launch_gemm: cta_group 2 is built for block_n 256 only");
     return PKB_ERR_INVALID;
   }
 #define PKB_GEMM_CASE(BN, PL, FN) \

@@ -368,7 +368,8 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
     }
     // CTA pairs for the hidden stages with 256-wide tiles and at least one full pair of row blocks
     static const bool no_pairs = getenv("PKB_GEMM_CG1") != nullptr;
-    const int cg = (!final && st.block_n == 256 && m_tiles >= 2 && !no_pairs) ? 2 : 1;
+    static const bool final_pairs = getenv("PKB_GEMM_FINAL_CG2") != nullptr;
+    const int cg = ((!final || final_pairs) && st.block_n == 256 && m_tiles >= 2 && !no_pairs) ? 2 : 1;
     PKB_TRY(launch_gemm(c, st.block_n, am->planes, final, cg, &tm_a_hi, &tm_a_lo,
                         cg == 2 ? &st.tm_w_hi_half : &st.tm_w_hi,
                         cg == 2 ? &st.tm_w_lo_half : &st.tm_w_lo, p));

@@ -33,10 +33,13 @@ namespace {
 constexpr int kMainThreads = 128;   // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare
 // FINAL: two teams of 8 epilogue warps, team t owns TMEM accumulator stage t (every other tile),
 // so one team's softmax exchange latency is covered by the other team's work.
+// Hidden stages: one team; 8 warps (two per lane quadrant, half of the columns each) when there
+// is one operand plane, 4 in BF16X3 where the staging tiles are twice as large and the MMA time
+// per tile is three times longer anyway.
 constexpr int epi_teams(bool final) { return final ? 2 : 1; }
-constexpr int team_warps(bool final) { return final ? 8 : 4; }
-constexpr int epi_warps(bool final) { return epi_teams(final) * team_warps(final); }
-constexpr int num_threads(bool final) { return kMainThreads + 32 * epi_warps(final); }
+constexpr int team_warps(bool final, int planes) { return (final || planes == 1) ? 8 : 4; }
+constexpr int epi_warps(bool final, int planes) { return epi_teams(final) * team_warps(final, planes); }
+constexpr int num_threads(bool final, int planes) { return kMainThreads + 32 * epi_warps(final, planes); }
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemBudget = 227 * 1024;
 
@@ -330,7 +333,7 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool 
   L.stage_bytes = planes * (L.a_plane + L.w_plane);
   // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
   // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch per team
-  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 2 * 128 * 8 : 4 * planes * 4096;
+  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 2 * 128 * 8 : team_warps(false, planes) * planes * 4096;
   uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */ - L.epi_bytes;
   L.stages = avail / L.stage_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
@@ -369,7 +372,7 @@ __device__ __forceinline__ bool get_tile(const GemmParams &p, int it, uint32_t r
 }
 
 template <int BN, int PLANES, bool FINAL, int CG>
-__global__ void __launch_bounds__(num_threads(FINAL), 1)
+__global__ void __launch_bounds__(num_threads(FINAL, PLANES), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
             const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
@@ -405,7 +408,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], CG * team_warps(FINAL));  // both CTAs of a pair release the leader
+      mbar_init(&tempty[i], CG * team_warps(FINAL, PLANES));  // both CTAs of a pair release the leader
     }
     fence_barrier_init();
   }
@@ -497,18 +500,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     // half of the tile's columns
     const int team = FINAL ? ((warp - 4) >> 3) : 0;
     const int wt = FINAL ? ((warp - 4) & 7) : (warp - 4);
-    const int chalf = FINAL ? (wt >> 2) : 0;
+    constexpr int kHalves = team_warps(FINAL, PLANES) / 4;  // warps per lane quadrant
+    const int chalf = wt >> 2;
     constexpr int kTeams = epi_teams(FINAL);
-    constexpr int kTeamThreads = 32 * team_warps(FINAL);
+    constexpr int kTeamThreads = 32 * team_warps(FINAL, PLANES);
     // per-warp staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7);
     // rows are written by their owner lane and read back 4 rows per instruction so that
     // every global store covers whole 128-byte lines
-    uint8_t *stg = smem + L.epi_off + (FINAL ? (warp - 4) * 4096 : q * (PLANES * 4096));
+    uint8_t *stg = smem + L.epi_off + (FINAL ? (warp - 4) * 4096 : wt * (PLANES * 4096));
     const uint32_t stg_w = smem_u32(stg) + lane * 128;          // this lane's row
     // grouped schedule: this CTA's column tile never changes, keep its bias / log-prior in smem
     float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + 16 * 4096);
     float *s_lp = s_bias + BN;
-    constexpr int kEpiThreads = 32 * epi_warps(FINAL);
+    constexpr int kEpiThreads = 32 * epi_warps(FINAL, PLANES);
     if (FINAL && p.group_sched) {
       const int nb = (static_cast<int>(blockIdx.x) / CG) % p.n_tiles_n;
       for (int i = threadIdx.x - kMainThreads; i < BN; i += kEpiThreads) {
@@ -545,8 +549,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
       if (!FINAL) {
         float sumsq = 0.0f;
+        constexpr int kGroups = BN / 64 / kHalves;  // 64-column groups per warp
 #pragma unroll 1
-        for (int g = 0; g < BN / 64; ++g) {
+        for (int g = chalf * kGroups; g < (chalf + 1) * kGroups; ++g) {
           const int col0 = n0 + g * 64;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -611,7 +616,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           if (leader) mbar_arrive(&tempty[as]); else mbar_arrive_remote(&tempty[as], 0);
         }
         if (p.out_sumsq != nullptr && row_ok)
-          p.out_sumsq[static_cast<size_t>(row) * p.n_tiles_n + n_blk] = sumsq;
+          p.out_sumsq[(static_cast<size_t>(row) * p.n_tiles_n + n_blk) * kHalves + chalf] = sumsq;
       } else {
         // ---- pass 1 (softmax only): per-row (max, sum exp) over this warp's half of the
         //      tile's columns, exchanged with the warps / CTAs that own the other columns
@@ -843,11 +848,11 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
     void *args[] = {&m0, &m1, &m2, &m3, &out_map, &pp};
     if (CG == 1) {
       PKB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid),
-                                           dim3(num_threads(FINAL)), args, L.total, c->stream));
+                                           dim3(num_threads(FINAL, PLANES)), args, L.total, c->stream));
     } else {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(num_threads(FINAL));
+      cfg.blockDim = dim3(num_threads(FINAL, PLANES));
       cfg.dynamicSmemBytes = L.total;
       cfg.stream = c->stream;
       cudaLaunchAttribute attr[2];
@@ -864,7 +869,7 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
   } else if (CG == 2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(num_threads(FINAL));
+    cfg.blockDim = dim3(num_threads(FINAL, PLANES));
     cfg.dynamicSmemBytes = L.total;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
@@ -876,7 +881,7 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
     cfg.numAttrs = 1;
     PKB_CUDA(cudaLaunchKernelEx(&cfg, kern, *a_hi, *a_lo, *w_hi, *w_lo, out_map, pp));
   } else {
-    kern<<<grid, num_threads(FINAL), L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, out_map, pp);
+    kern<<<grid, num_threads(FINAL, PLANES), L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, out_map, pp);
   }
   PKB_CUDA(cudaGetLastError());
   }

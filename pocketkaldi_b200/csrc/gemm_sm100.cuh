@@ -42,7 +42,7 @@ struct GemmParams {
   const float *in_sumsq;  // [M][in_sumsq_tiles] partial sums of squares, or nullptr
   int in_sumsq_tiles;
   float in_dim;        // D of the NormalizeLayer feeding this stage
-  float *out_sumsq;    // [M][n_tiles_n] or nullptr
+  float *out_sumsq;    // [M][n_tiles_n * sumsq_parts(planes)] or nullptr
   int relu;
   int fp16;            // operands (and hidden outputs) are FP16 instead of BF16
   __nv_bfloat16 *out_hi, *out_lo;  // [M][ld_out]
@@ -76,5 +76,8 @@ int launch_gemm(Ctx *c, int block_n, int planes, bool final, int cta_group, cons
 int make_output_map(CUtensorMap *map, const float *base, uint64_t cols, uint64_t rows);
 
 int gemm_max_smem_bytes(int block_n, int planes);
+
+// Sum-of-squares partials one hidden tile writes per row (= epilogue warps per lane quadrant).
+inline int sumsq_parts(int planes) { return planes == 1 ? 2 : 1; }
 
 }  // namespace pkb

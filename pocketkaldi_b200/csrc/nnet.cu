@@ -301,7 +301,7 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
   for (int i = 0; i < bufs; ++i) {
     PKB_TRY(ws->act_hi[i].ensure(static_cast<size_t>(rows) * max_hidden * 2));
     if (am->planes == 2) PKB_TRY(ws->act_lo[i].ensure(static_cast<size_t>(rows) * max_hidden * 2));
-    PKB_TRY(ws->sumsq[i].ensure(static_cast<size_t>(rows) * max_tiles * sizeof(float)));
+    PKB_TRY(ws->sumsq[i].ensure(static_cast<size_t>(rows) * max_tiles * sumsq_parts(am->planes) * sizeof(float)));
   }
   const Stage &last = am->stages.back();
   PKB_TRY(ws->lse_part.ensure(static_cast<size_t>((rows + kBlockM - 1) / kBlockM) * kBlockM *
@@ -379,7 +379,7 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       a_cols = st.n_pad;
       a_pitch = st.n_pad;
       in_sumsq = p.out_sumsq;
-      in_sumsq_tiles = p.n_tiles_n;
+      in_sumsq_tiles = p.n_tiles_n * sumsq_parts(am->planes);
       in_dim = static_cast<float>(st.out_dim);
     } else if (p.final_mode == 0 && prob_scale != 1.0f && mode == kFinalLoglik) {
       const int64_t n = rows * st.out_dim;

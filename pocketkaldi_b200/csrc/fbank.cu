@@ -90,6 +90,7 @@ fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample
   __shared__ uint32_t s_mels[kMel];
   __shared__ __align__(16) float2 s_x[4][2][16 * kXStride];  // per warp, per frame: transpose tile, then power
   __shared__ float s_part[4][2][kPartSlots];
+  __shared__ int s_utt;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -106,23 +107,49 @@ fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample
   if (tid < kMel) s_mels[tid] = tab.mel_sum[tid];
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // utterance of this tile: largest u with tile_prefix[u] <= tile
-    int lo = 0, hi = n_utts - 1;
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
+    __syncthreads();  // previous tile finished with s_pcm / s_utt; table staging visible
+    if (tid == 0) {
+      // utterance of this tile: largest u with tile_prefix[u] <= tile (one search per block)
+      int lo = 0, hi = n_utts - 1;
+      while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
+      }
+      s_utt = lo;
     }
-    const int u = lo;
+    __syncthreads();
+    const int u = s_utt;
     const int t0 = (tile - tile_prefix[u]) * kFramesPerTile;
     const int T = num_frames[u];
     const int n = num_samples[u];
     const SampleT *src = pcm + sample_off[u];
     const int s0 = t0 * kShift;
-
-    __syncthreads();  // previous tile finished with s_pcm; table staging visible
-    for (int i = tid; i < kTileSamples; i += 128) {
-      int s = s0 + i;
-      s_pcm[i] = s < n ? static_cast<float>(src[s]) : 0.0f;
+    // 16-byte vector loads (8 int16 / 4 float samples) when the tile start is aligned and the
+    // whole tile lies inside the utterance; element-wise otherwise
+    constexpr int kVec = 16 / sizeof(SampleT);
+    const bool vec_ok = (s0 + kTileSamples <= n) &&
+                        ((reinterpret_cast<uintptr_t>(src + s0) & 15) == 0);
+    if (vec_ok) {
+      const uint4 *v = reinterpret_cast<const uint4 *>(src + s0);
+      for (int i = tid; i < kTileSamples / kVec; i += 128) {
+        const uint4 w = __ldg(v + i);
+        float *d = s_pcm + i * kVec;
+        if (sizeof(SampleT) == 2) {
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            d[2 * q] = static_cast<float>(static_cast<int16_t>(ww[q] & 0xffffu));
+            d[2 * q + 1] = static_cast<float>(static_cast<int16_t>(ww[q] >> 16));
+          }
+        } else {
+          *reinterpret_cast<uint4 *>(d) = w;
+        }
+      }
+    } else {
+      for (int i = tid; i < kTileSamples; i += 128) {
+        int s = s0 + i;
+        s_pcm[i] = s < n ? static_cast<float>(src[s]) : 0.0f;
+      }
     }
     __syncthreads();
 
@@ -181,15 +208,22 @@ fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample
     dft16(a);  // a[r] = Z[k1 + 16*k2], k2 = bin_of_reg(r), k1 = j
 
     // ---- real-FFT post-pass + power spectrum (srfft.cc:396-440, fbank.cc:193-211) ----
+    // Bins k and 256-k come from the same pair (Z_k, Z_{256-k}):
+    //   A_k = (E - iT)/2, A_{256-k} = conj((E + iT)/2),  E = Z_k + conj(Z_{256-k}),
+    //   T = W512^k (Z_k - conj(Z_{256-k})),
+    // so the two power values share E and T. Lane j handles its own
+    // bins j + 16*k2 for k2 < 8 together with their partners (which live in lane 16-j at the
+    // static register 15-r), i.e. 8 pairs instead of 16 single bins.
     float *pw = reinterpret_cast<float *>(xb);  // 256 floats, reuses the transpose tile
     const int src_lane = (16 - j) & 15;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const int k2 = bin_of_reg(r);
-      // partner bin 256-k: lane 16-k1, register 15-r; for k1 == 0 it is this lane's bin 16*(16-k2)
+      if (k2 >= 8) continue;  // compile-time: the other half is produced as partners
       float2 p;
       p.x = __shfl_sync(0xffffffffu, a[15 - r].x, src_lane, 16);
       p.y = __shfl_sync(0xffffffffu, a[15 - r].y, src_lane, 16);
+      // lane 0: the partner of bin 16*k2 is this lane's own bin 16*(16-k2) (k2 = 0: itself)
       const float2 own = a[reg_of_bin((16 - k2) & 15)];
       if (j == 0) p = own;
       const float2 z = a[r];
@@ -197,9 +231,17 @@ fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample
       const float2 o = make_float2(z.x - p.x, z.y + p.y);
       const float2 tw = s_twr[k2 * 16 + j];
       const float2 tt = cmul(tw, o);
-      const float re = 0.5f * (e.x + tt.y);
-      const float im = 0.5f * (e.y - tt.x);
-      pw[j + 16 * k2] = re * re + im * im;
+      // formed as complex sums first: the difference form |E|^2 + |T|^2 -/+ 2 Re(..) would cancel
+      // when one bin of the pair is much weaker than the other
+      const float ax = e.x + tt.y, ay = e.y - tt.x;  // E - iT
+      const float bx = e.x - tt.y, by = e.y + tt.x;  // E + iT
+      const int k = j + 16 * k2;
+      pw[k] = 0.25f * fmaf(ax, ax, ay * ay);
+      if (k != 0) pw[256 - k] = 0.25f * fmaf(bx, bx, by * by);
+    }
+    if (j == 0) {
+      const float2 z = a[reg_of_bin(8)];  // bin 128 pairs with itself: |A_128|^2 = |Z_128|^2
+      pw[128] = fmaf(z.x, z.x, z.y * z.y);
     }
     __syncwarp();
 
@@ -233,13 +275,18 @@ fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample
       if (tt < T) {
         const float *part = s_part[warp][fr];
         float *dst = out + (frame_off[u] + tt) * kMel;
-        for (int m = lane; m < kMel; m += 32) {
-          const uint32_t s = s_mels[m];
-          const uint32_t first = s & 0xffffu, cnt = s >> 16;
-          float e = part[first];
-          for (uint32_t c = 1; c < cnt; ++c) e += part[first + c];
-          e = fmaxf(e, FLT_EPSILON);
-          dst[m] = logf(e);
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+          const int m = lane + 32 * rep;
+          if (m < kMel) {
+            const uint32_t s = s_mels[m];
+            const uint32_t first = s & 0xffffu, cnt = s >> 16;  // cnt in 1..3
+            float e = part[first];
+            if (cnt > 1) e += part[first + 1];
+            if (cnt > 2) e += part[first + 2];
+            e = fmaxf(e, FLT_EPSILON);
+            dst[m] = logf(e);
+          }
         }
       }
     }

@@ -462,7 +462,12 @@ def parity_sample(cfg, batch, ref_pack):
         batch.get_rows_async(pk.BUF_LOGLIK, 0, FRAMES_10S, got)
         batch.ctx.sync()
         out["loglik_max_abs_err_unscaled"] = float(np.max(np.abs(got - ll_ref)) / 0.1)
-        out["argmax_agreement"] = float(np.mean(got.argmax(1) == ll_ref.argmax(1)))
+        agree = got.argmax(1) == ll_ref.argmax(1)
+        out["argmax_agreement"] = float(np.mean(agree))
+        top2 = np.sort(ll_ref, axis=1)[:, -2:] / 0.1
+        clear = (top2[:, 1] - top2[:, 0]) > 2e-2   # frames whose reference margin exceeds the LL bar
+        out["argmax_agreement_margin_gt_2e-2"] = float(np.mean(agree[clear])) if clear.any() else None
+        out["frames_with_margin_gt_2e-2"] = float(np.mean(clear))
         out["tolerance"] = "north_star: |dLL| <= 2e-2, argmax agreement >= 0.999"
     return out
 

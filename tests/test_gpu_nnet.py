@@ -152,3 +152,81 @@ def test_fp16_mode_meets_loglik_tolerance(ctx, oracle):
     for o, r in zip(am.compute_batch(feats), ref):
         assert np.max(np.abs(o - r)) < LL_TOL
         assert np.mean(o.argmax(1) == r.argmax(1)) >= 0.99
+
+
+@pytest.mark.parametrize("in_ctx,hidden,n_hidden,pdfs,normalize", [
+    ((0, 0), 8, 1, 10, False),      # tiny, P % 4 != 0 -> scalar output path, no splice
+    ((1, 2), 100, 2, 7, True),      # asymmetric context, odd sizes, normalize
+    ((5, 5), 130, 1, 129, False),   # N just above one 128-tile
+    ((3, 3), 260, 2, 257, True),    # N just above one 256-tile
+    ((5, 5), 64, 0, 300, False),    # single linear + softmax
+])
+def test_odd_shapes_vs_oracle(ctx, oracle, in_ctx, hidden, n_hidden, pdfs, normalize):
+    left, right = in_ctx
+    rng = np.random.default_rng(hidden * 1000 + pdfs)
+    layers = formats.make_dnn(rng, 40 * (left + right + 1), hidden, n_hidden, pdfs, normalize=normalize)
+    prior = rng.uniform(0.5, 1.5, pdfs).astype(np.float32)
+    prior /= prior.sum()
+    feats = [(rng.standard_normal((n, 40)) * 2.5).astype(np.float32) for n in (1, 129, 2, 300)]
+    am = pk.AcousticModel(ctx, pk.PREC_BF16X3).from_layers(layers, prior, left, right)
+    outs = am.compute_batch(feats, 0.1)
+    for f, o in zip(feats, outs):
+        ref = oracle.decodable(f, layers, prior, left, right, 0.1)
+        assert o.shape == ref.shape
+        assert np.max(np.abs(o - ref)) < LL_TOL * 0.1
+        assert np.mean(o.argmax(1) == ref.argmax(1)) >= ARGMAX_MIN
+
+
+def test_nnet_propagate_without_softmax_and_odd_input_dim(ctx, oracle):
+    # Nnet::Propagate on a stack that ends in a linear layer (raw outputs), input dim 37
+    rng = np.random.default_rng(5)
+    layers = formats.make_dnn(rng, 37, 50, 1, 21)[:-1]
+    x = rng.standard_normal((77, 37)).astype(np.float32)
+    y = pk.Nnet(ctx).from_layers(layers).Propagate(x)
+    ref = oracle.nnet(x, layers)
+    assert y.shape == ref.shape == (77, 21)
+    assert np.max(np.abs(y - ref)) < 1e-4
+
+
+def test_config3_size_properties(ctx, golden):
+    # config-3 net on 48 x 10 s through the device-resident pipeline: size-independent
+    # properties instead of a CPU oracle -- (1) posteriors renormalise: sum_p prior_p *
+    # exp(ll_p / scale) == 1 per frame, (2) utterances are independent: the same utterance ids
+    # give the same bits at other batch positions, (3) BF16X3 vs FP16 vs BF16 orderings agree
+    rng = np.random.default_rng(0)
+    layers = formats.make_dnn(rng, 440, 1024, 6, 3000)
+    prior = rng.uniform(0.5, 1.5, 3000).astype(np.float32)
+    prior /= prior.sum()
+    n_utts, n = 48, 160000
+    scale = 0.1
+    outs = {}
+    for name, prec in (("bf16x3", pk.PREC_BF16X3), ("fp16", pk.PREC_FP16), ("bf16", pk.PREC_BF16)):
+        am = pk.AcousticModel(ctx, prec).from_layers(layers, prior, 5, 5)
+        b = pk.Batch(ctx, [n] * n_utts, golden["cmvn_stats"], am, prob_scale=scale)
+        b.synth_pcm(1234, 0)
+        b.run(pk.STAGE_ALL)
+        ll = b.get(pk.BUF_LOGLIK).reshape(n_utts, 998, 3000)
+        assert np.isfinite(ll).all()
+        post = np.exp(ll.astype(np.float64) / scale) * prior.astype(np.float64)
+        tol = {"bf16x3": 1e-4, "fp16": 1e-4, "bf16": 1e-4}[name]
+        assert np.max(np.abs(post.sum(axis=2) - 1.0)) < tol
+        b2 = pk.Batch(ctx, [n] * 3, golden["cmvn_stats"], am, prob_scale=scale)
+        b2.synth_pcm(1234, 20)
+        b2.run(pk.STAGE_ALL)
+        assert np.array_equal(b2.get(pk.BUF_LOGLIK).reshape(3, 998, 3000), ll[20:23])
+        chk = b.checksum(pk.BUF_LOGLIK)
+        assert abs(chk - float(ll.astype(np.float64).sum())) < 1e-6 * abs(chk)
+        outs[name] = ll
+        b.close()
+        b2.close()
+        am.close()
+    # single-MMA modes against the parity mode over 47 904 frames x 3000 pdfs. With the speech
+    # CMVN statistics applied to synthetic noise the features (and activations) are larger than in
+    # the bench distribution and the FP16 tail maximum (observed 4.6e-2 unscaled) exceeds the 2e-2
+    # bar it meets there (tools/precision_stats.py: 9e-3); bounded here, reported in DESIGN.md.
+    ref = outs["bf16x3"]
+    d16 = np.abs(outs["fp16"] - ref) / scale
+    assert d16.max() < 1e-1 and d16.mean() < 5e-3
+    assert np.mean(outs["fp16"].argmax(2) == ref.argmax(2)) > 0.995
+    assert np.abs(outs["bf16"] - ref).max() / scale < 1.0
+    assert np.mean(outs["bf16"].argmax(2) == ref.argmax(2)) > 0.97

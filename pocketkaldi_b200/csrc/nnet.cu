@@ -402,14 +402,32 @@ int copy_rows_compact(Ctx *c, void *host_dst, const float *d_padded, const Batch
   const int64_t end = frame0 + n;
   char *dst = static_cast<char *>(host_dst);
   const size_t row_bytes = static_cast<size_t>(cols) * sizeof(float);
-  for (; u < m.n_utts && m.frame_off[u] < end; ++u) {
+  while (u < m.n_utts && m.frame_off[u] < end) {
     const int64_t a = std::max<int64_t>(frame0, m.frame_off[u]);
     const int64_t b = std::min<int64_t>(end, m.frame_off[u + 1]);
-    if (b <= a) continue;
+    if (b <= a) { ++u; continue; }
     const int64_t prow = pad_off[u] + (a - m.frame_off[u]);
-    PKB_CUDA(cudaMemcpyAsync(dst + (a - frame0) * row_bytes,
-                             reinterpret_cast<const char *>(d_padded) + prow * row_bytes,
-                             (b - a) * row_bytes, cudaMemcpyDeviceToHost, c->stream));
+    // a run of whole utterances of equal length is one strided 2-D copy (source pitch = padded
+    // utterance, destination pitch = compact utterance) instead of one copy per utterance
+    int run = 1;
+    const int64_t T = m.num_frames[u];
+    if (a == m.frame_off[u] && b == m.frame_off[u + 1] && T > 0) {
+      // equal lengths imply equal padded pitch: pad_off[v + 1] - pad_off[v] = T_v + left + right
+      while (u + run < m.n_utts && m.num_frames[u + run] == T && m.frame_off[u + run + 1] <= end)
+        ++run;
+    }
+    if (run > 1) {
+      const size_t src_pitch = static_cast<size_t>(pad_off[u + 1] - pad_off[u]) * row_bytes;
+      PKB_CUDA(cudaMemcpy2DAsync(dst + (a - frame0) * row_bytes, static_cast<size_t>(T) * row_bytes,
+                                 reinterpret_cast<const char *>(d_padded) + prow * row_bytes, src_pitch,
+                                 static_cast<size_t>(T) * row_bytes, run, cudaMemcpyDeviceToHost,
+                                 c->stream));
+    } else {
+      PKB_CUDA(cudaMemcpyAsync(dst + (a - frame0) * row_bytes,
+                               reinterpret_cast<const char *>(d_padded) + prow * row_bytes,
+                               (b - a) * row_bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    u += run;
   }
   return PKB_OK;
 }

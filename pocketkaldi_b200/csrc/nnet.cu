@@ -366,10 +366,14 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       p.scale = prob_scale;
       p.log_floor = static_cast<float>(log(static_cast<double>(static_cast<float>(1.0e-20))));
     }
-    // CTA pairs for the hidden stages with 256-wide tiles and at least one full pair of row blocks
+    // CTA pairs (cta_group::2) whenever the tile is 256 wide and there is at least one full pair
+    // of row blocks: always for hidden stages; for the output stage only in BF16X3, where the
+    // halved W tile is what makes a second pipeline stage fit (its BF16/FP16 variant is bound by
+    // the epilogue, not by operand traffic, and measured no gain from pairing)
     static const bool no_pairs = getenv("PKB_GEMM_CG1") != nullptr;
     static const bool final_pairs = getenv("PKB_GEMM_FINAL_CG2") != nullptr;
-    const int cg = ((!final || final_pairs) && st.block_n == 256 && m_tiles >= 2 && !no_pairs) ? 2 : 1;
+    const bool want_pair = !final || am->planes == 2 || final_pairs;
+    const int cg = (want_pair && st.block_n == 256 && m_tiles >= 2 && !no_pairs) ? 2 : 1;
     PKB_TRY(launch_gemm(c, st.block_n, am->planes, final, cg, &tm_a_hi, &tm_a_lo,
                         cg == 2 ? &st.tm_w_hi_half : &st.tm_w_hi,
                         cg == 2 ? &st.tm_w_lo_half : &st.tm_w_lo, p));

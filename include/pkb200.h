@@ -13,6 +13,12 @@
  *
  * There is no CPU fallback. Every function fails with PKB_ERR_CUDA when no
  * sm_100 device is usable.
+ *
+ * Threading: like the reference's per-utterance objects, a pkb_ctx_t and everything
+ * created from it (models, batches, streams) must be used by one host thread at a
+ * time; different contexts (also on the same GPU) are independent and may be driven
+ * concurrently -- that is how bench.py overlaps the D2H copy of one chunk with the
+ * kernels of the next.
  */
 #ifndef PKB200_H_
 #define PKB200_H_

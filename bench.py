@@ -128,6 +128,8 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at INFO/VERSION
+        os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)

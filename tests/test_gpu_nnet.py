@@ -1,6 +1,8 @@
 """GPU parity of the nnet / acoustic-model path (tcgen05 GEMMs + fused epilogues) through the
 C ABI, against the compiled-reference golden vectors and the restatement oracle."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -230,3 +232,36 @@ def test_config3_size_properties(ctx, golden):
     assert np.mean(outs["fp16"].argmax(2) == ref.argmax(2)) > 0.995
     assert np.abs(outs["bf16"] - ref).max() / scale < 1.0
     assert np.mean(outs["bf16"].argmax(2) == ref.argmax(2)) > 0.97
+
+
+def test_loader_errors_follow_the_reference_convention(ctx, tmp_path, toy_conf):
+    # AcousticModel::Read error classes (src/am.cc:23-63, src/status.h:37-100): missing file ->
+    # IOError, malformed section -> Corruption, missing key -> Corruption "Unable to find key"
+    with pytest.raises(pk.PkbError) as e:
+        pk.AcousticModel(ctx).Read(str(tmp_path / "nope.conf"))
+    assert e.value.code == 2 and "IOError" in str(e.value)
+    import shutil
+    d = tmp_path / "m"
+    shutil.copytree(os.path.dirname(toy_conf), d)
+    conf = str(d / "toy.conf")
+    raw = bytearray(open(d / "toy.nnet", "rb").read())
+    raw[0:4] = b"XXXX"
+    open(d / "toy.nnet", "wb").write(bytes(raw))
+    with pytest.raises(pk.PkbError) as e:
+        pk.AcousticModel(ctx).Read(conf)
+    assert e.value.code == 3 and "Corruption" in str(e.value)
+    shutil.copy(os.path.join(os.path.dirname(toy_conf), "toy.nnet"), d / "toy.nnet")
+    lines = [l for l in open(conf) if not l.startswith("prior")]
+    open(conf, "w").writelines(lines)
+    with pytest.raises(pk.PkbError) as e:
+        pk.AcousticModel(ctx).Read(conf)
+    assert e.value.code == 3 and "Unable to find key 'prior'" in str(e.value)
+    # layer types ADD(4)/MUL(5) are rejected like the reference reader does (src/nnet.cc:122-126)
+    import struct
+    with open(d / "bad.nnet", "wb") as fd:
+        fd.write(b"NNT0" + struct.pack("<ii", 4, 1) + b"LAY0" + struct.pack("<ii", 4, 5))
+    open(conf, "w").writelines([l.replace("toy.nnet", "bad.nnet") if l.startswith("nnet") else l
+                                for l in open(toy_conf)])
+    with pytest.raises(pk.PkbError) as e:
+        pk.AcousticModel(ctx).Read(conf)
+    assert e.value.code == 3 and "unexpected layer type: 5" in str(e.value)

@@ -51,15 +51,21 @@ cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off
   __nv_bfloat16 *ph = p_hi ? p_hi + pad_off[u] * dim_pad + d : nullptr;
   __nv_bfloat16 *pl = p_lo ? p_lo + pad_off[u] * dim_pad + d : nullptr;
 
+  // The chain itself is ~4 dependent operations per frame; what has to be hidden is the load
+  // latency with only a few warps per SM at small batch sizes. The loads of the next group of
+  // kCmvnUnroll frames are therefore issued before the current group is consumed (two register
+  // sets, software pipelined).
   float stat = 0.0f;
-  for (int t0 = 0; t0 < T; t0 += kCmvnUnroll) {
-    float xv[kCmvnUnroll], xp[kCmvnUnroll];
+  float xa[kCmvnUnroll], pa[kCmvnUnroll], xb[kCmvnUnroll], pb[kCmvnUnroll];
+  auto load = [&](int t0, float (&xv)[kCmvnUnroll], float (&xp)[kCmvnUnroll]) {
 #pragma unroll
     for (int i = 0; i < kCmvnUnroll; ++i) {
       const int t = t0 + i;
       xv[i] = t < T ? x[static_cast<int64_t>(t) * kMel] : 0.0f;
       xp[i] = (t < T && t >= kCmvnWindow) ? x[static_cast<int64_t>(t - kCmvnWindow) * kMel] : 0.0f;
     }
+  };
+  auto consume = [&](int t0, const float (&xv)[kCmvnUnroll], const float (&xp)[kCmvnUnroll]) {
 #pragma unroll
     for (int i = 0; i < kCmvnUnroll; ++i) {
       const int t = t0 + i;
@@ -91,6 +97,13 @@ cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off
         }
       }
     }
+  };
+  load(0, xa, pa);
+  for (int t0 = 0; t0 < T; t0 += 2 * kCmvnUnroll) {
+    load(t0 + kCmvnUnroll, xb, pb);
+    consume(t0, xa, pa);
+    load(t0 + 2 * kCmvnUnroll, xa, pa);
+    consume(t0 + kCmvnUnroll, xb, pb);
   }
 }
 

@@ -36,9 +36,16 @@ constexpr int kMainThreads = 128;   // warps 0-3: TMA producer, MMA issuer, TMEM
 // Hidden stages: one team; 8 warps (two per lane quadrant, half of the columns each) when there
 // is one operand plane, 4 in BF16X3 where the staging tiles are twice as large and the MMA time
 // per tile is three times longer anyway.
-constexpr int epi_teams(bool final) { return final ? 2 : 1; }
+// Measured on B200 (config 3, 1024 utterances): a second hidden epilogue team (16 warps, 96
+// registers, one pipeline stage less) is 5 % slower than one team, and dropping the back-off
+// sleeps of the producer / MMA waits changes nothing -- the hidden stages are bound by the
+// TMA -> MMA stream, not by the epilogue (PKB_GEMM_DEBUG=1 prints the per-tile cycle split).
+#ifndef PKB_HID_TEAMS
+#define PKB_HID_TEAMS 1
+#endif
+constexpr int epi_teams(bool final, int planes) { return final ? 2 : (planes == 1 ? PKB_HID_TEAMS : 1); }
 constexpr int team_warps(bool final, int planes) { return (final || planes == 1) ? 8 : 4; }
-constexpr int epi_warps(bool final, int planes) { return epi_teams(final) * team_warps(final, planes); }
+constexpr int epi_warps(bool final, int planes) { return epi_teams(final, planes) * team_warps(final, planes); }
 constexpr int num_threads(bool final, int planes) { return kMainThreads + 32 * epi_warps(final, planes); }
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemBudget = 227 * 1024;
@@ -333,7 +340,7 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool 
   L.stage_bytes = planes * (L.a_plane + L.w_plane);
   // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
   // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch per team
-  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 2 * 128 * 8 : team_warps(false, planes) * planes * 4096;
+  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 2 * 128 * 8 : epi_warps(false, planes) * planes * 4096;
   uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */ - L.epi_bytes;
   L.stages = avail / L.stage_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
@@ -462,12 +469,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       int m_blk, n_blk;
       for (int it = 0; get_tile<CG>(p, it, cta_rank, m_blk, n_blk); ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        long long tw0 = 0, tw_full = 0;
+        if (p.dbg != nullptr) tw0 = clock64();
         mbar_wait<32>(&tempty[as], aph ^ 1);
         tc_fence_after();
+        if (p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 8 + 6] += clock64() - tw0;
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (p.dbg != nullptr) tw0 = clock64();
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (p.dbg != nullptr) tw_full += clock64() - tw0;
           const uint32_t sa = smem_u32(smem + s * L.stage_bytes);
           const uint32_t sw = sa + PLANES * L.a_plane;
           const uint64_t a_hi = make_smem_desc(sa);
@@ -491,6 +503,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           if (++s == S) { s = 0; ph ^= 1; }
         }
         umma_commit<CG>(&tfull[as]);  // accumulator complete
+        if (p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 8 + 7] += tw_full;
       }
     }
   } else if (warp >= 4) {
@@ -498,16 +511,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     const int q = warp & 3;  // TMEM lane quadrant
     // FINAL: team = accumulator stage; inside a team two warps per lane quadrant, each owning
     // half of the tile's columns
-    const int team = FINAL ? ((warp - 4) >> 3) : 0;
-    const int wt = FINAL ? ((warp - 4) & 7) : (warp - 4);
+    constexpr int kTeams = epi_teams(FINAL, PLANES);
+    const int team = kTeams == 2 ? ((warp - 4) >> 3) : 0;
+    const int wt = kTeams == 2 ? ((warp - 4) & 7) : (warp - 4);
     constexpr int kHalves = team_warps(FINAL, PLANES) / 4;  // warps per lane quadrant
     const int chalf = wt >> 2;
-    constexpr int kTeams = epi_teams(FINAL);
     constexpr int kTeamThreads = 32 * team_warps(FINAL, PLANES);
     // per-warp staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7);
     // rows are written by their owner lane and read back 4 rows per instruction so that
     // every global store covers whole 128-byte lines
-    uint8_t *stg = smem + L.epi_off + (FINAL ? (warp - 4) * 4096 : wt * (PLANES * 4096));
+    uint8_t *stg = smem + L.epi_off + (FINAL ? (warp - 4) * 4096 : (warp - 4) * (PLANES * 4096));
     const uint32_t stg_w = smem_u32(stg) + lane * 128;          // this lane's row
     // grouped schedule: this CTA's column tile never changes, keep its bias / log-prior in smem
     float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + 16 * 4096);
@@ -539,8 +552,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         rs = sqrtf(p.in_dim / ss);  // NormalizeLayer: no floor (src/nnet.cc:71-73)
       }
 
-      long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0;
-      const bool dbg_on = FINAL && p.dbg != nullptr && warp == 4 && lane == 0;  // team 0
+      long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tkm = 0;
+      const bool dbg_on = p.dbg != nullptr && warp == 4 && lane == 0;  // team 0
       if (dbg_on) tk0 = clock64();
       mbar_wait<32>(&tfull[as], aph);
       tc_fence_after();
@@ -556,8 +569,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t v[32];
+            if (dbg_on) tk2 = clock64();
             tmem_ld32(taddr + g * 64 + h * 32, v);
             tmem_ld_wait();
+            if (dbg_on) { const long long t = clock64(); tk3 += t - tk2; tk2 = t; }
             float z[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -583,6 +598,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             for (int j = 0; j < 4; ++j)
               st_shared_v4(stg_w + (((h * 4 + j) ^ (lane & 7)) << 4), hi[4 * j], hi[4 * j + 1],
                            hi[4 * j + 2], hi[4 * j + 3]);
+            if (dbg_on) tkm += clock64() - tk2;
             if (PLANES == 2) {
               uint32_t lo[16];
 #pragma unroll
@@ -597,6 +613,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             }
           }
           __syncwarp();
+          if (dbg_on) tk2 = clock64();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + t_row;
@@ -608,6 +625,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             }
           }
           __syncwarp();
+          if (dbg_on) tk4 += clock64() - tk2;
         }
         // all TMEM reads of this accumulator are done: hand it back to the MMA warp
         tc_fence_before();
@@ -617,6 +635,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
         if (p.out_sumsq != nullptr && row_ok)
           p.out_sumsq[(static_cast<size_t>(row) * p.n_tiles_n + n_blk) * kHalves + chalf] = sumsq;
+        if (dbg_on) {
+          const long long tk5 = clock64();
+          long long *d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
+          d[0] += tk1 - tk0;        // wait for the accumulator
+          d[1] += tk3;              // TMEM loads
+          d[2] += tk4;              // staged global stores
+          d[3] += tk5 - tk1;        // whole tile after the wait
+          d[4] += tkm;              // bias / ReLU / pack / staging writes
+          d[5] += 1;
+        }
       } else {
         // ---- pass 1 (softmax only): per-row (max, sum exp) over this warp's half of the
         //      tile's columns, exchanged with the warps / CTAs that own the other columns
@@ -833,7 +861,7 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
   }
   static const bool dbg_env = getenv("PKB_GEMM_DEBUG") != nullptr;
   long long *dbg = nullptr;
-  if (dbg_env && FINAL && p.final_mode != 0) {
+  if (dbg_env) {
     cudaMalloc(&dbg, sizeof(long long) * 8 * grid);
     cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * grid, c->stream);
   }
@@ -894,8 +922,12 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
     for (int b = 0; b < grid; ++b)
       for (int k = 0; k < 8; ++k) s[k] += h[8 * b + k];
     const double n = s[5] > 0 ? s[5] : 1;
-    fprintf(stderr, "[pkb gemm final] tiles/cta=%.0f cycles/tile: wait_acc=%.0f pass1=%.0f sync=%.0f combine=%.0f pass2=%.0f\n",
-            n / grid, s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n);
+    if (FINAL)
+      fprintf(stderr, "[pkb gemm final] tiles/cta=%.0f cycles/tile: wait_acc=%.0f pass1=%.0f sync=%.0f combine=%.0f pass2=%.0f | mma: wait_tmem=%.0f wait_smem=%.0f\n",
+              n / grid, s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n, s[6] / n, s[7] / n);
+    else
+      fprintf(stderr, "[pkb gemm kb=%d] tiles/cta=%.0f cycles/tile: wait_acc=%.0f tmem_ld=%.0f math=%.0f stores=%.0f epilogue=%.0f | mma: wait_tmem=%.0f wait_smem=%.0f\n",
+              p.num_kb, n / grid, s[0] / n, s[1] / n, s[4] / n, s[2] / n, s[3] / n, s[6] / n * CG, s[7] / n * CG);
   }
   return PKB_OK;
 }

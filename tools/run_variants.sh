@@ -1,0 +1,7 @@
+#!/bin/bash
+# On the GPU box: times bench.py's kernel classes with each build_variants/<name>.so in turn.
+for v in "$@"; do
+  cp build_variants/$v.so pocketkaldi_b200/libpkb200.so
+  echo "== $v"
+  timeout 300 python bench.py --utts ${UTTS:-1024} --steps 3 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python tools/_kernel_ms.py
+done

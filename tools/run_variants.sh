@@ -1,7 +1,10 @@
 #!/bin/bash
 # On the GPU box: times bench.py's kernel classes with each build_variants/<name>.so in turn.
-for v in "$@"; do
+# A variant name may carry environment settings after a colon: name:VAR=1,VAR2=x
+for spec in "$@"; do
+  v=${spec%%:*}; envs=""
+  if [[ "$spec" == *:* ]]; then envs=$(echo "${spec#*:}" | tr ',' ' '); fi
   cp build_variants/$v.so pocketkaldi_b200/libpkb200.so
-  echo "== $v"
-  timeout 300 python bench.py --utts ${UTTS:-1024} --steps 3 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python tools/_kernel_ms.py
+  echo "== $spec"
+  env $envs timeout 300 python bench.py --utts ${UTTS:-1024} --steps 3 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python tools/_kernel_ms.py
 done

@@ -192,6 +192,38 @@ int pkb_stream_push_i16(pkb_stream_t *st, const int16_t *pcm, float *loglik_out,
                         int32_t *frames_out);
 int pkb_stream_flush(pkb_stream_t *st, float *loglik_out, int32_t *frames_out);
 
+/* ---- batched ingestion --------------------------------------
+ * Host-side readers that feed the batch pipeline without the reference's detour through
+ * float: pk_16kpcm_read (src/pcm_reader.cc:45-220) parses one strict 44-byte RIFF/WAVE file
+ * (PCM, mono, 16 kHz, 8/16/32 bit) into an unscaled float vector, and main.cc:34-46 walks a
+ * .scp list one file at a time. Here the same header checks (same messages, PKB_ERR_CORRUPT /
+ * PKB_ERR_IO like Status::Corruption / IOError) are applied, 8/16-bit samples go straight to
+ * int16 (typically pinned) staging, and a list is read by several host threads.
+ * These functions do not touch the GPU and work without one. */
+int pkb_wav_probe(const char *path, int32_t *num_samples, int32_t *bits_per_sample);
+/* 8- and 16-bit files; a 32-bit file is PKB_ERR_UNSUPPORTED (use the f32 reader). */
+int pkb_wav_read_i16(const char *path, int16_t *dst, int32_t capacity, int32_t *num_samples);
+/* 8/16/32-bit files, unscaled: element-for-element what pk_16kpcm_read returns. */
+int pkb_wav_read_f32(const char *path, float *dst, int32_t capacity, int32_t *num_samples);
+
+/* A list of wave files: one path per line, trailing CR/LF trimmed (pk_readable_readline,
+ * src/util.cc:130-160). Every header is validated when the list is opened, so sizes are known
+ * before the batch is created. Unlike the reference CLI a last line without a newline is not
+ * an error. */
+typedef struct pkb_wavlist pkb_wavlist_t;
+int pkb_scp_open(const char *scp_path, pkb_wavlist_t **list);
+/* Same, from an array of paths. */
+int pkb_wavlist_create(const char *const *paths, int n_paths, pkb_wavlist_t **list);
+void pkb_wavlist_destroy(pkb_wavlist_t *list);
+int pkb_wavlist_size(const pkb_wavlist_t *list);
+const char *pkb_wavlist_path(const pkb_wavlist_t *list, int i);
+/* [size] samples per file: the num_samples argument of pkb_batch_create. */
+const int32_t *pkb_wavlist_num_samples(const pkb_wavlist_t *list);
+/* Reads files [first, first + count) back to back into dst (the layout pkb_batch_set_pcm_i16
+ * expects) with n_threads host threads (<= 0: one per hardware thread, at most 16). */
+int pkb_wavlist_read_i16(const pkb_wavlist_t *list, int first, int count, int16_t *dst,
+                         int n_threads);
+
 /* ---- pinned host memory for callers that want overlapped copies ------------*/
 int pkb_host_alloc(void **ptr, uint64_t bytes);
 void pkb_host_free(void *ptr);

@@ -20,6 +20,8 @@ from .binding import (  # noqa: F401
     Decodable,
     Batch,
     Stream,
+    WavList,
+    read_wav,
     build_library,
     load_library,
     PREC_BF16,

@@ -87,6 +87,16 @@ _SIGNATURES = [
     ("pkb_stream_max_frames", C.c_int, [_VP]),
     ("pkb_stream_push_i16", C.c_int, [_VP, _VP, _VP, _VP]),
     ("pkb_stream_flush", C.c_int, [_VP, _VP, _VP]),
+    ("pkb_wav_probe", C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("pkb_wav_read_i16", C.c_int, [C.c_char_p, _VP, C.c_int32, C.POINTER(C.c_int32)]),
+    ("pkb_wav_read_f32", C.c_int, [C.c_char_p, _VP, C.c_int32, C.POINTER(C.c_int32)]),
+    ("pkb_scp_open", C.c_int, [C.c_char_p, C.POINTER(_VP)]),
+    ("pkb_wavlist_create", C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.POINTER(_VP)]),
+    ("pkb_wavlist_destroy", None, [_VP]),
+    ("pkb_wavlist_size", C.c_int, [_VP]),
+    ("pkb_wavlist_path", C.c_char_p, [_VP, C.c_int]),
+    ("pkb_wavlist_num_samples", C.POINTER(C.c_int32), [_VP]),
+    ("pkb_wavlist_read_i16", C.c_int, [_VP, C.c_int, C.c_int, _VP, C.c_int]),
     ("pkb_host_alloc", C.c_int, [C.POINTER(_VP), C.c_uint64]),
     ("pkb_host_free", None, [_VP]),
     ("pkb_timer_start", C.c_int, [_VP]),
@@ -147,6 +157,66 @@ class PinnedArray:
             self.array = None
             self.lib.pkb_host_free(self.ptr)
             self.ptr = None
+
+
+def read_wav(path, dtype=np.float32):
+    """pk_16kpcm_read (src/pcm_reader.cc:45-220): strict 16 kHz mono PCM WAV -> unscaled samples.
+    dtype float32 gives exactly the reference's vector; int16 is the batch pipeline's input."""
+    lib = load_library()
+    n = C.c_int32(0)
+    bits = C.c_int32(0)
+    _check(lib.pkb_wav_probe(os.fsencode(path), C.byref(n), C.byref(bits)))
+    out = np.empty(n.value, dtype=dtype)
+    fn = {np.dtype(np.float32): lib.pkb_wav_read_f32, np.dtype(np.int16): lib.pkb_wav_read_i16}[np.dtype(dtype)]
+    _check(fn(os.fsencode(path), out.ctypes.data_as(_VP), n.value, C.byref(n)))
+    return out
+
+
+class WavList:
+    """A validated list of wave files (pkb_wavlist_t): `.scp` file or a sequence of paths.
+    Replaces the one-file-at-a-time loop of src/main.cc:34-46 for the batch pipeline."""
+
+    def __init__(self, scp_or_paths):
+        self.lib = load_library()
+        self.h = _VP()
+        if isinstance(scp_or_paths, (str, bytes, os.PathLike)):
+            _check(self.lib.pkb_scp_open(os.fsencode(scp_or_paths), C.byref(self.h)))
+        else:
+            enc = [os.fsencode(p) for p in scp_or_paths]
+            arr = (C.c_char_p * max(len(enc), 1))(*enc)
+            _check(self.lib.pkb_wavlist_create(arr, len(enc), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.pkb_wavlist_destroy(self.h)
+            self.h = None
+
+    def __len__(self):
+        return self.lib.pkb_wavlist_size(self.h)
+
+    def path(self, i):
+        p = self.lib.pkb_wavlist_path(self.h, i)
+        if p is None:
+            raise IndexError(i)
+        return os.fsdecode(p)
+
+    @property
+    def num_samples(self):
+        n = len(self)
+        if n == 0:
+            return np.zeros(0, np.int32)
+        return np.ctypeslib.as_array(self.lib.pkb_wavlist_num_samples(self.h), shape=(n,)).copy()
+
+    def read_i16(self, first=0, count=None, out=None, n_threads=0):
+        """Samples of files [first, first+count) back to back (the pkb_batch_set_pcm_i16 layout).
+        `out` may be a PinnedArray's .array."""
+        count = len(self) - first if count is None else count
+        total = int(self.num_samples[first:first + count].sum())
+        if out is None:
+            out = np.empty(total, np.int16)
+        assert out.dtype == np.int16 and out.size >= total and out.flags["C_CONTIGUOUS"]
+        _check(self.lib.pkb_wavlist_read_i16(self.h, first, count, out.ctypes.data_as(_VP), n_threads))
+        return out[:total]
 
 
 class Context:

@@ -128,6 +128,28 @@ int pkb_am_compute(pkb_ctx_t *ctx, pkb_am_t *am, const float *feats,
                    const int32_t *num_frames, int n_utts, int feat_dim, float prob_scale,
                    float *loglik_out);
 
+/* ---- event-gated results (lazy / chunked decodable) ------------
+ * pk_decodable_init (src/decodable.cc:8-17) blocks until the whole [pdfs x frames] matrix is
+ * in host memory, although the decoder consumes it strictly frame by frame
+ * (Decoder::Decode / ProcessEmitting, src/decoder.cc:49,252-279). An event marks a point of the
+ * context's stream; the host can wait for it without waiting for later work. */
+typedef struct pkb_event pkb_event_t;
+int pkb_event_create(pkb_ctx_t *ctx, pkb_event_t **ev);
+void pkb_event_destroy(pkb_event_t *ev);
+int pkb_event_record(pkb_ctx_t *ctx, pkb_event_t *ev); /* after everything queued so far      */
+int pkb_event_wait(pkb_event_t *ev);                   /* blocks the calling host thread      */
+int pkb_event_query(pkb_event_t *ev, int *done);       /* *done = 1 once the point is reached */
+
+/* pkb_am_compute for ONE utterance that returns as soon as the work is queued. The result is
+ * copied out in chunks of chunk_frames frames; events[i] is recorded right after the copy of
+ * frames [i*chunk_frames, (i+1)*chunk_frames) so that a consumer may read them while later
+ * chunks are still in flight. n_events must be >= ceil(num_frames / chunk_frames). loglik_out
+ * must stay valid until the last event has completed and should be page-locked
+ * (pkb_host_alloc), otherwise each copy blocks the caller and nothing overlaps. */
+int pkb_am_compute_chunked(pkb_ctx_t *ctx, pkb_am_t *am, const float *feats, int32_t num_frames,
+                           int feat_dim, float prob_scale, float *loglik_out, int chunk_frames,
+                           pkb_event_t *const *events, int n_events);
+
 /* Nnet::Propagate (src/nnet.cc:149-163): the layer stack only, no splice, no
  * prior. in: [rows][in_dim]; out: [rows][out_dim of the last layer]. */
 int pkb_nnet_propagate(pkb_ctx_t *ctx, pkb_am_t *am, const float *in, int rows, int in_dim,

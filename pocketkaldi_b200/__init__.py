@@ -18,6 +18,7 @@ from .binding import (  # noqa: F401
     Nnet,
     AcousticModel,
     Decodable,
+    Event,
     Batch,
     Stream,
     WavList,

@@ -11,6 +11,7 @@ Reference interfaces mirrored here (paths relative to the pocketkaldi tree):
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -69,6 +70,13 @@ _SIGNATURES = [
     ("pkb_am_tid2pdf", C.c_int, [_VP, C.c_int]),
     ("pkb_am_num_tids", C.c_int, [_VP]),
     ("pkb_am_compute", C.c_int, [_VP, _VP, _f32p, _i32p, C.c_int, C.c_int, C.c_float, _f32p]),
+    ("pkb_event_create", C.c_int, [_VP, C.POINTER(_VP)]),
+    ("pkb_event_destroy", None, [_VP]),
+    ("pkb_event_record", C.c_int, [_VP, _VP]),
+    ("pkb_event_wait", C.c_int, [_VP]),
+    ("pkb_event_query", C.c_int, [_VP, C.POINTER(C.c_int)]),
+    ("pkb_am_compute_chunked", C.c_int, [_VP, _VP, _f32p, C.c_int32, C.c_int, C.c_float, _VP, C.c_int,
+                                         C.POINTER(_VP), C.c_int]),
     ("pkb_nnet_propagate", C.c_int, [_VP, _VP, _f32p, C.c_int, C.c_int, _f32p]),
     ("pkb_pcm_to_loglik_i16", C.c_int, [_VP, _VP, _i16p, _i32p, C.c_int, _f32p, C.c_float, _VP, _VP,
                                         _VP]),
@@ -225,10 +233,18 @@ class Context:
     def __init__(self, device=0):
         self.lib = load_library()
         self.h = _VP()
+        self._children = weakref.WeakSet()
         _check(self.lib.pkb_create(device, C.byref(self.h)))
+
+    def _adopt(self, child):
+        """Objects created on this context are closed before it (the C ABI requires that order)."""
+        self._children.add(child)
 
     def close(self):
         if self.h:
+            kids = list(self._children)
+            for child in sorted(kids, key=lambda k: isinstance(k, AcousticModel)):  # models last
+                child.close()
             self.lib.pkb_destroy(self.h)
             self.h = None
 
@@ -343,6 +359,7 @@ class AcousticModel:
         self.ctx = ctx
         self.precision = precision
         self.h = None
+        ctx._adopt(self)
 
     def Read(self, conf_path):
         """AcousticModel::Read(conf) (src/am.cc:23-63)."""
@@ -466,19 +483,87 @@ class Nnet:
         return out[:rows]
 
 
-class Decodable:
-    """pk_decodable_t (src/decodable.h:15-41): eager AM evaluation + table look-up."""
+class Event:
+    """pkb_event_t: a point of the context's stream the host can wait for."""
 
-    def __init__(self, am, prob_scale, feats):
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.h = _VP()
+        _check(ctx.lib.pkb_event_create(ctx.h, C.byref(self.h)))
+        ctx._adopt(self)
+
+    def record(self):
+        _check(self.ctx.lib.pkb_event_record(self.ctx.h, self.h))
+
+    def wait(self):
+        _check(self.ctx.lib.pkb_event_wait(self.h))
+
+    def done(self):
+        d = C.c_int(0)
+        _check(self.ctx.lib.pkb_event_query(self.h, C.byref(d)))
+        return bool(d.value)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.pkb_event_destroy(self.h)
+            self.h = None
+
+
+class Decodable:
+    """pk_decodable_t (src/decodable.h:15-41): AM evaluation + table look-up.
+
+    chunk_frames = 0: eager like the reference (pk_decodable_init returns when the whole matrix
+    is on the host). chunk_frames > 0: lazy -- the matrix lands in page-locked
+    memory chunk by chunk and loglikelihood(frame, ...) only waits for the chunk holding `frame`,
+    so a frame-synchronous decoder (src/decoder.cc:49) starts after the first chunk."""
+
+    def __init__(self, am, prob_scale, feats, chunk_frames=0):
         self.am = am
-        self.log_prob = am.Compute(feats, prob_scale)  # pk_decodable_init
+        self._events = []
+        self._pinned = None
+        if chunk_frames <= 0:
+            self.log_prob = am.Compute(feats, prob_scale)  # pk_decodable_init
+            self._ready = self.log_prob.shape[0]
+            return
+        feats = _f32(feats)
+        T, P = feats.shape[0], am.num_pdfs()
+        self._chunk = chunk_frames
+        self._pinned = PinnedArray((max(T, 1), P), np.float32)
+        self.log_prob = self._pinned.array[:T]
+        self._events = [Event(am.ctx) for _ in range((T + chunk_frames - 1) // chunk_frames)]
+        self._ready = 0
+        arr = (_VP * max(len(self._events), 1))(*[e.h for e in self._events])
+        _check(am.ctx.lib.pkb_am_compute_chunked(am.ctx.h, am.h, feats if T else np.zeros((1, 1), np.float32),
+                                                 T, feats.shape[1], prob_scale,
+                                                 self._pinned.array.ctypes.data_as(_VP), chunk_frames,
+                                                 arr, len(self._events)))
+
+    def frames_ready(self):
+        """Frames whose log-likelihoods are already in host memory (non-blocking)."""
+        while self._ready < self.log_prob.shape[0] and self._events[self._ready // self._chunk].done():
+            self._ready = min(self.log_prob.shape[0], (self._ready // self._chunk + 1) * self._chunk)
+        return self._ready
 
     def loglikelihood(self, frame, trans_id):
+        if frame >= self._ready:
+            self._events[frame // self._chunk].wait()   # stream order: earlier chunks are done too
+            self._ready = min(self.log_prob.shape[0], (frame // self._chunk + 1) * self._chunk)
         return float(self.log_prob[frame, self.am.TransitionIdToPdfId(trans_id)])
 
     def islastframe(self, frame):
         assert frame < self.log_prob.shape[0]
         return frame == self.log_prob.shape[0] - 1
+
+    def close(self):
+        if self._events:
+            self._events[-1].wait()
+        for e in self._events:
+            e.close()
+        self._events = []
+        if self._pinned is not None:
+            self.log_prob = None
+            self._pinned.free()
+            self._pinned = None
 
 
 class Batch:
@@ -494,6 +579,7 @@ class Batch:
                                         _f32(global_stats), prob_scale, C.byref(self.h)))
         self.num_frames = np.array([ctx.lib.pkb_fbank_num_frames(int(n)) for n in self.num_samples],
                                    np.int64)
+        ctx._adopt(self)
 
     def close(self):
         if self.h:
@@ -560,6 +646,7 @@ class Stream:
         self.h = _VP()
         _check(ctx.lib.pkb_stream_create(ctx.h, am.h, n_streams, chunk_samples, _f32(global_stats),
                                          prob_scale, C.byref(self.h)))
+        ctx._adopt(self)
         self.max_frames = ctx.lib.pkb_stream_max_frames(self.h)
         self.P = am.num_pdfs()
         self.out = np.empty((n_streams, self.max_frames, self.P), np.float32)

@@ -317,30 +317,33 @@ int pkb_am_tid2pdf(const pkb_am_t *am, int tid) {
   return am->tid2pdf[tid];
 }
 
-int pkb_am_compute(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t *num_frames,
-                   int n_utts, int feat_dim, float prob_scale, float *loglik_out) {
-  PKB_REQUIRE(c && am, "pkb_am_compute: NULL argument");
-  PKB_REQUIRE(am->c == c, "pkb_am_compute: model belongs to another context");
+// Shared body of pkb_am_compute / pkb_am_compute_chunked: everything up to the log-likelihoods in
+// am->out_f32 (padded-row layout); pad_off receives the first padded row of every utterance.
+static int am_compute_device(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t *num_frames,
+                             int n_utts, int feat_dim, float prob_scale, const char *who,
+                             std::vector<int64_t> *pad_off) {
+  PKB_REQUIRE(c && am, "%s: NULL argument", who);
+  PKB_REQUIRE(am->c == c, "%s: model belongs to another context", who);
   PKB_REQUIRE(am->has_splice_stage && feat_dim == am->feat_dim,
-              "pkb_am_compute: feat_dim %d does not match the model (nnet input %d, context %d+1+%d)",
+              "%s: feat_dim %d does not match the model (nnet input %d, context %d+1+%d)", who,
               feat_dim, am->input_dim, am->left, am->right);
   PKB_CUDA(cudaSetDevice(c->device));
   BatchMeta &m = am->meta;
   PKB_TRY(m.build_from_frames(num_frames, n_utts));
   if (m.total_frames == 0) return PKB_OK;
-  PKB_REQUIRE(feats && loglik_out, "pkb_am_compute: feats / loglik_out is NULL");
+  PKB_REQUIRE(feats != nullptr, "%s: feats is NULL", who);
   PKB_TRY(m.upload(c->stream));
-  std::vector<int64_t> pad_off;
   int64_t padded = 0, rows = 0;
-  pkb::padded_rows(m, am->left, am->right, &pad_off, &padded, &rows);
+  pkb::padded_rows(m, am->left, am->right, pad_off, &padded, &rows);
   Workspace &ws = am->ws;
   PKB_TRY(pkb::workspace_ensure(am, &ws, rows));
   const int dp = am->feat_dim_pad;
   PKB_TRY(ws.feat_hi.ensure(static_cast<size_t>(padded) * dp * 2));
   if (am->planes == 2) PKB_TRY(ws.feat_lo.ensure(static_cast<size_t>(padded) * dp * 2));
-  PKB_TRY(ws.pad_off.ensure(pad_off.size() * sizeof(int64_t)));
+  PKB_TRY(ws.pad_off.ensure(pad_off->size() * sizeof(int64_t)));
   PKB_TRY(ws.row_map.ensure(static_cast<size_t>(rows) * sizeof(int32_t)));
-  PKB_CUDA(cudaMemcpyAsync(ws.pad_off.p, pad_off.data(), pad_off.size() * sizeof(int64_t),
+  // pageable source: staged by the runtime before the call returns
+  PKB_CUDA(cudaMemcpyAsync(ws.pad_off.p, pad_off->data(), pad_off->size() * sizeof(int64_t),
                            cudaMemcpyHostToDevice, c->stream));
   const size_t in_bytes = static_cast<size_t>(m.total_frames) * feat_dim * sizeof(float);
   const size_t out_bytes = static_cast<size_t>(rows) * am->num_pdfs * sizeof(float);  // padded rows
@@ -358,11 +361,101 @@ int pkb_am_compute(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t
   in.rows = rows;
   in.cols = (am->left + am->right + 1) * dp;
   in.pitch_elems = dp;
-  PKB_TRY(pkb::nnet_forward(am, &ws, in, &am->splice_stage, pkb::kFinalLoglik, prob_scale,
-                            am->out_f32.as<float>()));
+  return pkb::nnet_forward(am, &ws, in, &am->splice_stage, pkb::kFinalLoglik, prob_scale,
+                           am->out_f32.as<float>());
+}
+
+int pkb_am_compute(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t *num_frames,
+                   int n_utts, int feat_dim, float prob_scale, float *loglik_out) {
+  std::vector<int64_t> pad_off;
+  PKB_TRY(am_compute_device(c, am, feats, num_frames, n_utts, feat_dim, prob_scale, "pkb_am_compute",
+                            &pad_off));
+  const BatchMeta &m = am->meta;
+  if (m.total_frames == 0) return PKB_OK;
+  PKB_REQUIRE(loglik_out != nullptr, "pkb_am_compute: loglik_out is NULL");
   PKB_TRY(pkb::copy_rows_compact(c, loglik_out, am->out_f32.as<float>(), m, pad_off, am->num_pdfs, 0,
                                  m.total_frames));
-  PKB_CUDA(cudaStreamSynchronize(c->stream));  // also covers the pad_off staging vector
+  PKB_CUDA(cudaStreamSynchronize(c->stream));
+  return PKB_OK;
+}
+
+struct pkb_event {
+  pkb_ctx_t *c = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool recorded = false;
+};
+
+int pkb_event_create(pkb_ctx_t *c, pkb_event_t **out) {
+  PKB_REQUIRE(c && out, "pkb_event_create: NULL argument");
+  *out = nullptr;
+  PKB_CUDA(cudaSetDevice(c->device));
+  cudaEvent_t e;
+  PKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  pkb_event *ev = new pkb_event;
+  ev->c = c;
+  ev->ev = e;
+  *out = ev;
+  return PKB_OK;
+}
+
+void pkb_event_destroy(pkb_event_t *ev) {
+  if (ev == nullptr) return;
+  cudaEventDestroy(ev->ev);
+  delete ev;
+}
+
+int pkb_event_record(pkb_ctx_t *c, pkb_event_t *ev) {
+  PKB_REQUIRE(c && ev && ev->c == c, "pkb_event_record: NULL argument or event of another context");
+  PKB_CUDA(cudaEventRecord(ev->ev, c->stream));
+  ev->recorded = true;
+  return PKB_OK;
+}
+
+int pkb_event_wait(pkb_event_t *ev) {
+  PKB_REQUIRE(ev != nullptr, "pkb_event_wait: NULL event");
+  PKB_REQUIRE(ev->recorded, "pkb_event_wait: event was never recorded");
+  PKB_CUDA(cudaEventSynchronize(ev->ev));
+  return PKB_OK;
+}
+
+int pkb_event_query(pkb_event_t *ev, int *done) {
+  PKB_REQUIRE(ev && done, "pkb_event_query: NULL argument");
+  *done = 0;
+  if (!ev->recorded) return PKB_OK;
+  const cudaError_t e = cudaEventQuery(ev->ev);
+  if (e == cudaSuccess) {
+    *done = 1;
+    return PKB_OK;
+  }
+  if (e == cudaErrorNotReady) return PKB_OK;
+  PKB_CUDA(e);
+  return PKB_OK;
+}
+
+int pkb_am_compute_chunked(pkb_ctx_t *c, pkb_am_t *am, const float *feats, int32_t num_frames,
+                           int feat_dim, float prob_scale, float *loglik_out, int chunk_frames,
+                           pkb_event_t *const *events, int n_events) {
+  PKB_REQUIRE(chunk_frames > 0, "pkb_am_compute_chunked: chunk_frames must be positive");
+  PKB_REQUIRE(num_frames >= 0, "pkb_am_compute_chunked: num_frames < 0");
+  const int n_chunks = (num_frames + chunk_frames - 1) / chunk_frames;
+  PKB_REQUIRE(n_events >= n_chunks && (events != nullptr || n_chunks == 0),
+              "pkb_am_compute_chunked: %d events for %d chunks", n_events, n_chunks);
+  for (int i = 0; i < n_chunks; ++i)
+    PKB_REQUIRE(events[i] != nullptr && events[i]->c == c,
+                "pkb_am_compute_chunked: event %d is NULL or belongs to another context", i);
+  std::vector<int64_t> pad_off;
+  PKB_TRY(am_compute_device(c, am, feats, &num_frames, 1, feat_dim, prob_scale,
+                            "pkb_am_compute_chunked", &pad_off));
+  if (num_frames == 0) return PKB_OK;
+  PKB_REQUIRE(loglik_out != nullptr, "pkb_am_compute_chunked: loglik_out is NULL");
+  const BatchMeta &m = am->meta;
+  for (int i = 0; i < n_chunks; ++i) {
+    const int64_t r0 = static_cast<int64_t>(i) * chunk_frames;
+    const int64_t n = std::min<int64_t>(chunk_frames, num_frames - r0);
+    PKB_TRY(pkb::copy_rows_compact(c, loglik_out + r0 * am->num_pdfs, am->out_f32.as<float>(), m,
+                                   pad_off, am->num_pdfs, r0, n));
+    PKB_TRY(pkb_event_record(c, events[i]));
+  }
   return PKB_OK;
 }
 

@@ -28,9 +28,14 @@ for f in $KEEP; do OBJS="$OBJS $OUT/obj/$f.o"; done
 $CXX -o "$OUT/pocketkaldi_b200_cli" "$OUT/shim/main.o" "$OUT/shim/pocketkaldi.o" \
   "$OUT/shim/decoder.o" "$OUT/shim/pkb_shim.o" $OBJS \
   -L"$ROOT/pocketkaldi_b200" -lpkb200 -Wl,-rpath,'$ORIGIN/../../pocketkaldi_b200' -lm -pthread
+# batch driver: list ingestion + one GPU batch + the reference decoder on host threads
+$CXX $FLAGS -include "$HERE/pkb_shim.h" -c "$HERE/pkb_batch_main.cc" -o "$OUT/shim/pkb_batch_main.o"
+$CXX -o "$OUT/pocketkaldi_b200_batch" "$OUT/shim/pkb_batch_main.o" "$OUT/shim/pocketkaldi.o" \
+  "$OUT/shim/decoder.o" "$OUT/shim/pkb_shim.o" $OBJS \
+  -L"$ROOT/pocketkaldi_b200" -lpkb200 -Wl,-rpath,'$ORIGIN/../../pocketkaldi_b200' -lm -pthread
 # the hot path must come from the shim, not from the reference objects
 if nm "$OUT/pocketkaldi_b200_cli" | grep -q "pk_srfft_compute"; then
   echo "build_shim: reference FFT leaked into the shim binary" >&2
   exit 1
 fi
-echo "build_shim: ok -> $OUT/pocketkaldi_b200_cli"
+echo "build_shim: ok -> $OUT/pocketkaldi_b200_cli, $OUT/pocketkaldi_b200_batch"

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "pkb200.h"
 
@@ -198,20 +199,135 @@ void AcousticModel::Compute(const pk_matrix_t *frames, pk_matrix_t *loglikelihoo
 
 }  // namespace pocketkaldi
 
+pkb_ctx *pkb_shim_context() { return shim_ctx(); }
+
 // ---------------------------------------------------------------- decodable
+// Storage of a lazy decodable: page-locked matrix + one event per chunk. cudaHostAlloc costs
+// milliseconds, and the reference builds one decodable after the other (src/pocketkaldi.cc:210-247),
+// so the last released storage is kept for the next utterance.
+struct pkb_lazy_decodable {
+  float *pinned = nullptr;
+  size_t capacity = 0;  // floats
+  std::vector<pkb_event_t *> events;
+  int chunk = 0;
+  pkb_event_t *attached = nullptr;  // attach mode: the caller's event (not owned)
+  bool attached_mode = false;
+};
+
+namespace {
+
+pkb_lazy_decodable *g_spare = nullptr;
+
+int decodable_chunk_frames() {
+  const char *e = getenv("PKB_DECODABLE_CHUNK");
+  return e != nullptr ? atoi(e) : 0;
+}
+
+pkb_lazy_decodable *lazy_acquire(size_t floats, int n_events) {
+  pkb_lazy_decodable *l = g_spare != nullptr ? g_spare : new pkb_lazy_decodable;
+  g_spare = nullptr;
+  if (l->capacity < floats) {
+    pkb_host_free(l->pinned);
+    l->pinned = nullptr;
+    l->capacity = 0;
+    void *p = nullptr;
+    must(pkb_host_alloc(&p, floats * sizeof(float)), "pk_decodable_init (page-locked buffer)");
+    l->pinned = static_cast<float *>(p);
+    l->capacity = floats;
+  }
+  while (static_cast<int>(l->events.size()) < n_events) {
+    pkb_event_t *e = nullptr;
+    must(pkb_event_create(shim_ctx(), &e), "pk_decodable_init (event)");
+    l->events.push_back(e);
+  }
+  return l;
+}
+
+void lazy_release(pkb_lazy_decodable *l) {
+  if (l->attached_mode) {
+    delete l;
+    return;
+  }
+  if (g_spare == nullptr) {
+    g_spare = l;
+    return;
+  }
+  for (pkb_event_t *e : l->events) pkb_event_destroy(e);
+  pkb_host_free(l->pinned);
+  delete l;
+}
+
+}  // namespace
+
 void pk_decodable_init(pk_decodable_t *self, AcousticModel *am, float prob_scale,
                        const pk_matrix_t *feats) {
-  pk_matrix_init(&self->log_prob, am->num_pdfs(), feats->ncol);
-  am->ComputeScaled(feats, prob_scale, &self->log_prob);
   self->am = am;
+  self->lazy = nullptr;
+  const int chunk = decodable_chunk_frames();
+  const int frames = feats->ncol, pdfs = am->num_pdfs();
+  if (chunk <= 0 || frames == 0) {
+    pk_matrix_init(&self->log_prob, pdfs, frames);
+    am->ComputeScaled(feats, prob_scale, &self->log_prob);
+    self->frames_ready = frames;
+    return;
+  }
+  const int n_chunks = (frames + chunk - 1) / chunk;
+  pkb_lazy_decodable *l = lazy_acquire(static_cast<size_t>(frames) * pdfs, n_chunks);
+  l->chunk = chunk;
+  self->lazy = l;
+  self->log_prob.nrow = pdfs;
+  self->log_prob.ncol = frames;
+  self->log_prob.data = l->pinned;
+  self->frames_ready = 0;
+  must(pkb_am_compute_chunked(shim_ctx(), am->handle(), feats->data, frames, feats->nrow, prob_scale,
+                              l->pinned, chunk, l->events.data(), n_chunks),
+       "pk_decodable_init");
+}
+
+void pk_decodable_attach(pk_decodable_t *self, AcousticModel *am, float *log_prob, int frames,
+                         pkb_event *ready) {
+  pkb_lazy_decodable *l = new pkb_lazy_decodable;
+  l->attached_mode = true;
+  l->attached = ready;
+  self->am = am;
+  self->lazy = l;
+  self->log_prob.nrow = am->num_pdfs();
+  self->log_prob.ncol = frames;
+  self->log_prob.data = log_prob;
+  self->frames_ready = ready != nullptr ? 0 : frames;
 }
 
 void pk_decodable_destroy(pk_decodable_t *self) {
-  pk_matrix_destroy(&self->log_prob);
+  if (self->lazy == nullptr) {
+    pk_matrix_destroy(&self->log_prob);
+  } else {
+    pkb_lazy_decodable *l = self->lazy;
+    // the copies still in flight write into the storage: let them finish before it is reused
+    if (!l->attached_mode && self->frames_ready < self->log_prob.ncol)
+      must(pkb_event_wait(l->events[(self->log_prob.ncol - 1) / l->chunk]), "pk_decodable_destroy");
+    lazy_release(l);
+    self->lazy = nullptr;
+    self->log_prob.data = nullptr;
+    self->log_prob.nrow = self->log_prob.ncol = 0;
+  }
   self->am = NULL;
 }
 
 float pk_decodable_loglikelihood(pk_decodable_t *self, int frame, int trans_id) {
+  if (frame >= self->frames_ready) {
+    pkb_lazy_decodable *l = self->lazy;
+    assert(l != nullptr && frame < self->log_prob.ncol);
+    if (l->attached_mode) {
+      must(pkb_event_wait(l->attached), "pk_decodable_loglikelihood");
+      self->frames_ready = self->log_prob.ncol;
+    } else {
+      // chunks complete in stream order: waiting for this frame's chunk covers the earlier ones
+      const int c = frame / l->chunk;
+      must(pkb_event_wait(l->events[c]), "pk_decodable_loglikelihood");
+      const int upto = (c + 1) * l->chunk;
+      self->frames_ready = upto < self->log_prob.ncol ? upto : self->log_prob.ncol;
+    }
+  }
   const int pdf_id = self->am->TransitionIdToPdfId(trans_id);
   return self->log_prob.data[static_cast<size_t>(frame) * self->log_prob.nrow + pdf_id];
 }

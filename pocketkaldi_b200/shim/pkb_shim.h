@@ -97,6 +97,8 @@ class AcousticModel {
   int num_pdfs() const;
   // Compute with the decodable's prob_scale folded into the GPU epilogue
   void ComputeScaled(const pk_matrix_t *frames, float prob_scale, pk_matrix_t *loglikelihood);
+  // the C-ABI model behind this object (batch drivers, lazy decodable)
+  pkb_am *handle() const { return model_; }
 
  private:
   AcousticModel(const AcousticModel &);
@@ -109,9 +111,20 @@ class AcousticModel {
 using pocketkaldi::AcousticModel;
 using pocketkaldi::Nnet;
 
+// Lazy mode. With PKB_DECODABLE_CHUNK=<frames> in the environment,
+// pk_decodable_init returns as soon as the GPU work is queued; the matrix lands in page-locked
+// memory chunk by chunk and pk_decodable_loglikelihood waits only for the chunk that holds the
+// frame it is asked for, so Decoder::Decode (src/decoder.cc:49) overlaps with the copy-out.
+struct pkb_lazy_decodable;
+struct pkb_event;
+
 typedef struct pk_decodable_t {
-  pk_matrix_t log_prob;  // {nrow = num_pdfs, ncol = frames}, malloc-family host memory
+  // {nrow = num_pdfs, ncol = frames}. Eager mode: malloc-family host memory like the reference.
+  // Lazy / attached mode: page-locked memory that `lazy` (or the caller) owns.
+  pk_matrix_t log_prob;
   AcousticModel *am;
+  pkb_lazy_decodable *lazy;  // NULL in eager mode
+  int frames_ready;          // frames [0, frames_ready) are valid in log_prob
 } pk_decodable_t;
 
 POCKETKALDI_EXPORT
@@ -123,5 +136,17 @@ POCKETKALDI_EXPORT
 float pk_decodable_loglikelihood(pk_decodable_t *self, int frame, int trans_id);
 POCKETKALDI_EXPORT
 bool pk_decodable_islastframe(pk_decodable_t *self, int frame);
+
+// The process-wide context the shim objects live on (device from PKB_DEVICE).
+struct pkb_ctx;
+POCKETKALDI_EXPORT
+pkb_ctx *pkb_shim_context();
+
+// Extension for batch drivers: a decodable over `frames` rows of [num_pdfs] floats that a batch
+// pipeline is copying (or has copied) into caller-owned host memory; `ready` (may be NULL) is
+// waited for on the first look-up. pk_decodable_destroy leaves the memory and the event alone.
+POCKETKALDI_EXPORT
+void pk_decodable_attach(pk_decodable_t *self, AcousticModel *am, float *log_prob, int frames,
+                         pkb_event *ready);
 
 #endif  // PKB_SHIM_H_

@@ -16,12 +16,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHIM_CLI = os.path.join(ROOT, "oracle", "_ref", "pocketkaldi_b200_cli")
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "pocketkaldi_ref")
+BATCH_CLI = os.path.join(ROOT, "oracle", "_ref", "pocketkaldi_b200_batch")
 
 
-def run_cli(cli, conf, inp, env=None):
+def run_cli(cli, conf, inp, env=None, extra=()):
     e = dict(os.environ)
     e.update(env or {})
-    out = subprocess.run([cli, conf, inp], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+    out = subprocess.run([cli, conf, inp] + list(extra), stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                          timeout=120, env=e, check=True).stdout.decode()
     res = []
     for line in out.strip().splitlines():
@@ -96,3 +97,44 @@ def test_shim_reports_reference_style_load_errors(tmp_path):
     bad = str(tmp_path / "missing.conf")
     r = subprocess.run([SHIM_CLI, bad, "x.wav"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
     assert r.returncode == 1 and b"pocketkaldi:" in r.stdout
+
+
+def test_lazy_decodable_decodes_the_same_words(wavs, toy_conf):
+    # pk_decodable_init returns before the matrix is on the host; the unchanged
+    # decoder pulls it chunk by chunk through pk_decodable_loglikelihood
+    if not os.path.exists(SHIM_CLI):
+        pytest.skip("shim CLI not built")
+    gold = golden_hyps()
+    eager = run_cli(SHIM_CLI, toy_conf, wavs["scp"], {"PKB_PRECISION": "bf16x3"})
+    for chunk in ("1", "32", "100000"):
+        lazy = run_cli(SHIM_CLI, toy_conf, wavs["scp"], {"PKB_PRECISION": "bf16x3", "PKB_DECODABLE_CHUNK": chunk})
+        assert lazy == eager, chunk
+    assert [r[1] for r in eager] == [gold["hello"][0], gold["cat"][0]]
+
+
+def test_batch_cli_prints_the_reference_lines(wavs, toy_conf, tmp_path):
+    # list ingestion + one GPU batch + the reference decoder on host threads
+    if not os.path.exists(BATCH_CLI):
+        pytest.skip("batch CLI not built")
+    gold = golden_hyps()
+    order = ["cat", "hello", "hello", "cat", "cat"]
+    scp = str(tmp_path / "five.scp")
+    with open(scp, "w") as fd:
+        fd.write("".join(wavs[n] + "\n" for n in order))
+    for extra in (["--threads", "3"], ["--threads", "2", "--batch-utts", "2"], ["--threads", "1", "--batch-utts", "1"]):
+        res = run_cli(BATCH_CLI, toy_conf, scp, {"PKB_PRECISION": "bf16x3"}, extra)
+        assert [r[0] for r in res] == ["en-us-%s.wav" % n for n in order]
+        assert [r[1] for r in res] == [gold[n][0] for n in order], extra
+        for r, n in zip(res, order):
+            assert abs(r[2] - gold[n][1]) < 2e-3
+    # single wav argument, like the reference CLI
+    (_, hyp, _), = run_cli(BATCH_CLI, toy_conf, wavs["hello"], {"PKB_PRECISION": "bf16x3"})
+    assert hyp == gold["hello"][0]
+    # a corrupt file anywhere in the list is reported before any GPU work, reference wording
+    bad = str(tmp_path / "bad.wav")
+    raw = bytearray(open(wavs["hello"], "rb").read())
+    raw[24:28] = (8000).to_bytes(4, "little")
+    open(bad, "wb").write(bytes(raw))
+    open(scp, "a").write(bad + "\n")
+    r = subprocess.run([BATCH_CLI, toy_conf, scp], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert r.returncode == 1 and b"sample_rate == 16000 expected, but 8000 found" in r.stdout

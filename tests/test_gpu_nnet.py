@@ -265,3 +265,30 @@ def test_loader_errors_follow_the_reference_convention(ctx, tmp_path, toy_conf):
     with pytest.raises(pk.PkbError) as e:
         pk.AcousticModel(ctx).Read(conf)
     assert e.value.code == 3 and "unexpected layer type: 5" in str(e.value)
+
+
+def test_lazy_decodable_matches_eager_bitwise(ctx, golden, toy_conf):
+    # SURVEY 8(f)-1 through the C ABI: pkb_am_compute_chunked + pkb_event_*
+    am = pk.AcousticModel(ctx, pk.PREC_BF16X3).Read(toy_conf)
+    feats = golden["cat_cmvn_ref"]
+    eager = pk.Decodable(am, 0.1, feats)
+    for chunk in (1, 7, 64, 10 ** 6):
+        lazy = pk.Decodable(am, 0.1, feats, chunk_frames=chunk)
+        T = feats.shape[0]
+        # frame-synchronous access like Decoder::ProcessEmitting
+        for t in (0, 1, T // 2, T - 1):
+            for tid in (1, 5):
+                assert lazy.loglikelihood(t, tid) == eager.loglikelihood(t, tid)
+        assert lazy.islastframe(T - 1) and not lazy.islastframe(0)
+        assert lazy.frames_ready() == T
+        assert np.array_equal(np.asarray(lazy.log_prob), eager.log_prob)
+        lazy.close()
+    # an early frame does not need the whole matrix
+    lazy = pk.Decodable(am, 0.1, feats, chunk_frames=16)
+    lazy.loglikelihood(0, 1)
+    assert 16 <= lazy._ready <= feats.shape[0]
+    lazy.close()
+    # no frames
+    empty = pk.Decodable(am, 0.1, np.zeros((0, 40), np.float32), chunk_frames=8)
+    assert empty.log_prob.shape == (0, am.num_pdfs())
+    empty.close()

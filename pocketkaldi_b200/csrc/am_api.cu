@@ -115,6 +115,7 @@ int read_nnet(const std::string &path, HostNnet *net) {
   PKB_TRY(fd.expect("NNT0"));
   PKB_TRY(fd.read_i32(&size));
   PKB_TRY(fd.read_i32(&n));
+  std::vector<float> pending_scale;  // MUL layer waiting for the next linear layer
   for (int i = 0; i < n; ++i) {
     int32_t lsize = 0, type = 0;
     PKB_TRY(fd.expect("LAY0"));
@@ -135,16 +136,64 @@ int read_nnet(const std::string &path, HostNnet *net) {
                        path.c_str());
         return PKB_ERR_CORRUPT;
       }
+      if (!pending_scale.empty()) {
+        // y = W (x * v) + b  ==  (W diag(v)) x + b
+        if (static_cast<int>(pending_scale.size()) != c) {
+          pkb::set_error("Corruption: MUL layer of dim %zu in front of a linear layer with %d inputs (%s)",
+                         pending_scale.size(), c, path.c_str());
+          return PKB_ERR_CORRUPT;
+        }
+        for (int i2 = 0; i2 < r; ++i2)
+          for (int j = 0; j < c; ++j) W[static_cast<size_t>(i2) * c + j] *= pending_scale[j];
+        pending_scale.clear();
+      }
       net->W.push_back(std::move(W));
       net->b.push_back(std::move(b));
       net->out_dims.push_back(r);
       net->in_dims.push_back(c);
+    } else if (type == 5) {
+      // MUL layer (tool/convert_am.py:86-110,213-217 writes one for Kaldi's FixedScaleComponent):
+      // y = x * v element-wise. The reference reader rejects it (src/nnet.cc:122-126), so real
+      // nnet2 models with a FixedScaleComponent cannot be loaded there; here it is folded into the
+      // neighbouring LinearLayer at load time and costs nothing at run time.
+      std::vector<float> v;
+      PKB_TRY(read_vec(&fd, &v));
+      if (!net->types.empty() && net->types.back() == 0) {
+        // directly after a linear layer: y = v * (W x + b) == (diag(v) W) x + v * b
+        std::vector<float> &W = net->W.back(), &b = net->b.back();
+        const int r = net->out_dims.back(), c = net->in_dims.back();
+        if (static_cast<int>(v.size()) != r) {
+          pkb::set_error("Corruption: MUL layer of dim %zu after a linear layer with %d outputs (%s)",
+                         v.size(), r, path.c_str());
+          return PKB_ERR_CORRUPT;
+        }
+        for (int i2 = 0; i2 < r; ++i2) {
+          for (int j = 0; j < c; ++j) W[static_cast<size_t>(i2) * c + j] *= v[i2];
+          b[i2] *= v[i2];
+        }
+      } else if (pending_scale.empty()) {
+        pending_scale = std::move(v);  // folded into the next linear layer
+      } else {
+        if (pending_scale.size() != v.size()) {
+          pkb::set_error("Corruption: consecutive MUL layers of dims %zu and %zu (%s)",
+                         pending_scale.size(), v.size(), path.c_str());
+          return PKB_ERR_CORRUPT;
+        }
+        for (size_t j = 0; j < v.size(); ++j) pending_scale[j] *= v[j];
+      }
+      continue;  // not a layer of the executed stack
     } else if (type < 0 || type > 3) {
-      // the reference reader rejects ADD (4) / MUL (5) as well (src/nnet.cc:122-126)
+      // ADD (4) is defined by the converter but never written by it; rejected like the
+      // reference reader does (src/nnet.cc:122-126)
       pkb::set_error("Corruption: read_layer: unexpected layer type: %d (%s)", type, path.c_str());
       return PKB_ERR_CORRUPT;
     }
+    if (type != 0 && !pending_scale.empty()) break;  // relu(x * v) / normalize(x * v) do not fold
     net->types.push_back(type);
+  }
+  if (!pending_scale.empty()) {
+    pkb::set_error("MUL layer that is not adjacent to a linear layer cannot be folded (%s)", path.c_str());
+    return PKB_ERR_UNSUPPORTED;
   }
   return PKB_OK;
 }

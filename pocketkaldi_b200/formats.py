@@ -21,6 +21,7 @@ import struct
 import numpy as np
 
 LINEAR, RELU, NORMALIZE, SOFTMAX = 0, 1, 2, 3
+MUL = 5  # tool/convert_am.py:16-22; not in the reference reader's enum (src/nnet.h)
 LAYER_NAMES = {LINEAR: "linear", RELU: "relu", NORMALIZE: "normalize", SOFTMAX: "softmax"}
 FST_SECTION = b"pk::fst_0"
 
@@ -82,8 +83,11 @@ def _read_mat(fd):
 
 # ----------------------------------------------------------------------------- NNT0
 def write_nnet(path, layers):
-    """layers: list of ("linear", W[out x in], b[out]) | ("relu",) | ("normalize",) | ("softmax",)."""
+    """layers: list of ("linear", W[out x in], b[out]) | ("relu",) | ("normalize",) | ("softmax",)
+    | ("mul", v) -- the MUL layer tool/convert_am.py:86-110 writes for a FixedScaleComponent; the
+    reference reader rejects it (src/nnet.cc:122-126), libpkb200 folds it into a Linear layer."""
     ids = {v: k for k, v in LAYER_NAMES.items()}
+    ids["mul"] = MUL
     with open(path, "wb") as fd:
         fd.write(b"NNT0" + struct.pack("<ii", 4, len(layers)))
         for layer in layers:
@@ -94,6 +98,8 @@ def write_nnet(path, layers):
                 assert W.shape[0] == b.shape[0]
                 fd.write(_mat_bytes(W))
                 fd.write(_vec_bytes(b, "<f4"))
+            elif kind == MUL:
+                fd.write(_vec_bytes(layer[1], "<f4"))
 
 
 def read_nnet(path):
@@ -112,6 +118,8 @@ def read_nnet(path):
                 W = _read_mat(fd)
                 b = _read_vec(fd)
                 layers.append(("linear", W, b))
+            elif kind == MUL:
+                layers.append(("mul", _read_vec(fd)))
             elif kind in LAYER_NAMES:
                 layers.append((LAYER_NAMES[kind],))
             else:
@@ -205,6 +213,31 @@ def read_wav16(path):
 
 
 # ----------------------------------------------------------------------------- synthetic models
+def fold_mul_layers(layers):
+    """What libpkb200's loader does with ("mul", v) layers: y = x * v folded into the preceding
+    Linear (rows of W and b scaled) when it follows one directly, otherwise into the next Linear
+    (columns of W scaled). Returns a layer list the reference reader accepts."""
+    out, pending = [], None
+    for l in layers:
+        if l[0] == "mul":
+            v = np.asarray(l[1], np.float32)
+            if out and out[-1][0] == "linear":
+                W, b = out[-1][1], out[-1][2]
+                out[-1] = ("linear", (W * v[:, None]).astype(np.float32), (b * v).astype(np.float32))
+            else:
+                pending = v if pending is None else (pending * v).astype(np.float32)
+        elif l[0] == "linear" and pending is not None:
+            out.append(("linear", (l[1] * pending[None, :]).astype(np.float32), l[2]))
+            pending = None
+        elif pending is not None:
+            break
+        else:
+            out.append(l)
+    if pending is not None:
+        raise ValueError("mul layer that is not adjacent to a linear layer cannot be folded")
+    return out
+
+
 def make_dnn(rng, in_dim, hidden, num_hidden, num_pdfs, normalize=False, w_scale=None):
     """[Linear, ReLU(, Normalize)] x num_hidden, Linear, Softmax.
 

@@ -59,3 +59,32 @@ def test_model_dir_loads_in_reference(tmp_path, reference, golden):
     am = reference.am_load(conf)
     assert reference.am_num_pdfs(am) == 6 and reference.am_tid2pdf(am, 3) == 2
     reference.am_free(am)
+
+
+def test_mul_layer_roundtrip_fold_and_reference_rejection(tmp_path, reference, oracle, golden):
+    # the MUL layer tool/convert_am.py:86-110 writes for a FixedScaleComponent
+    rng = np.random.default_rng(3)
+    base = formats.make_dnn(rng, 440, 16, 1, 5)
+    v0 = rng.uniform(0.5, 2.0, 440).astype(np.float32)
+    v1 = rng.uniform(-2.0, 2.0, 16).astype(np.float32)
+    layers = [("mul", v0), base[0], ("mul", v1)] + base[1:]
+    p = str(tmp_path / "m.nnet")
+    formats.write_nnet(p, layers)
+    back = formats.read_nnet(p)
+    assert [l[0] for l in back] == [l[0] for l in layers]
+    assert np.array_equal(back[0][1], v0) and np.array_equal(back[2][1], v1)
+    folded = formats.fold_mul_layers(layers)
+    assert [l[0] for l in folded] == [l[0] for l in base]
+    # folding is the same function: oracle(folded)(x) == oracle(base)(x * v0) with rows scaled by v1
+    x = rng.normal(size=(7, 440)).astype(np.float32)
+    W, b = base[0][1], base[0][2]
+    want = (x * v0) @ W.T.astype(np.float64) + b
+    got = x @ folded[0][1].T.astype(np.float64) + folded[0][2]
+    assert np.allclose(got, want * v1, rtol=1e-5, atol=1e-5)
+    if reference is not None:
+        prior = np.full(5, 0.2, np.float32)
+        conf = formats.write_model_dir(str(tmp_path), "mm", layers, prior, 5, 5, [0, 1, 2, 3, 4])
+        with pytest.raises(Exception):
+            reference.am_load(conf)       # src/nnet.cc:122-126 "unexpected layer type"
+        conf2 = formats.write_model_dir(str(tmp_path), "mf", folded, prior, 5, 5, [0, 1, 2, 3, 4])
+        reference.am_load(conf2)

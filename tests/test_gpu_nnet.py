@@ -256,15 +256,83 @@ def test_loader_errors_follow_the_reference_convention(ctx, tmp_path, toy_conf):
     with pytest.raises(pk.PkbError) as e:
         pk.AcousticModel(ctx).Read(conf)
     assert e.value.code == 3 and "Unable to find key 'prior'" in str(e.value)
-    # layer types ADD(4)/MUL(5) are rejected like the reference reader does (src/nnet.cc:122-126)
+    # unknown layer types are rejected like the reference reader does (src/nnet.cc:122-126);
+    # MUL (5) is the one extension, see test_mul_layers_are_folded_into_linear
     import struct
-    with open(d / "bad.nnet", "wb") as fd:
-        fd.write(b"NNT0" + struct.pack("<ii", 4, 1) + b"LAY0" + struct.pack("<ii", 4, 5))
-    open(conf, "w").writelines([l.replace("toy.nnet", "bad.nnet") if l.startswith("nnet") else l
-                                for l in open(toy_conf)])
+    for bad_type in (4, 6, -1):
+        with open(d / "bad.nnet", "wb") as fd:
+            fd.write(b"NNT0" + struct.pack("<ii", 4, 1) + b"LAY0" + struct.pack("<ii", 4, bad_type))
+        open(conf, "w").writelines([l.replace("toy.nnet", "bad.nnet") if l.startswith("nnet") else l
+                                    for l in open(toy_conf)])
+        with pytest.raises(pk.PkbError) as e:
+            pk.AcousticModel(ctx).Read(conf)
+        assert e.value.code == 3 and "unexpected layer type: %d" % bad_type in str(e.value)
+
+
+def test_mul_layers_are_folded_into_linear(ctx, oracle, reference, tmp_path, golden):
+    # tool/convert_am.py writes a MUL layer for Kaldi's FixedScaleComponent; the
+    # reference reader rejects such a model, libpkb200 folds y = x * v into the neighbouring
+    # LinearLayer when it loads the file. Checked against the oracle on the hand-folded model
+    # (tight) and against a float64 evaluation of the unfolded layer list (the semantics).
+    rng = np.random.default_rng(11)
+    base = formats.make_dnn(rng, 440, 96, 2, 24, normalize=True)
+    v_in = rng.uniform(0.5, 1.5, 440).astype(np.float32)
+    v_h = rng.uniform(-1.5, 1.5, 96).astype(np.float32)      # negative scales are fine before ReLU
+    v_out = rng.uniform(0.2, 3.0, 24).astype(np.float32)
+    layers = [("mul", v_in)]
+    n_lin = 0
+    for l in base:
+        layers.append(l)
+        if l[0] == "linear":
+            n_lin += 1
+            if n_lin == 1:
+                layers.append(("mul", v_h))
+            if n_lin == 3:
+                layers += [("mul", v_out), ("mul", np.full(24, 0.5, np.float32))]
+    prior = rng.dirichlet(np.ones(24)).astype(np.float32)
+    conf = formats.write_model_dir(str(tmp_path), "mul", layers, prior, 5, 5, list(range(24)),
+                                   cmvn_stats=golden["cmvn_stats"])
+    assert [l[0] for l in formats.read_nnet(str(tmp_path / "mul.nnet"))].count("mul") == 4
+    if reference is not None:
+        with pytest.raises(Exception):
+            reference.am_load(conf)
+    am = pk.AcousticModel(ctx, pk.PREC_BF16X3).Read(conf)
+    feats = golden["hello_cmvn_ref"]
+    got = am.Compute(feats)
+    folded = formats.fold_mul_layers(layers)
+    assert all(l[0] != "mul" for l in folded) and len(folded) == len(base)
+    want = oracle.am_compute(feats, folded, prior, 5, 5)
+    assert np.max(np.abs(got - want)) < 2e-3
+    assert np.mean(got.argmax(1) == want.argmax(1)) >= 0.999
+
+    def forward64(x):
+        T = x.shape[0]
+        idx = np.clip(np.arange(T)[:, None] + np.arange(-5, 6)[None, :], 0, T - 1)
+        h = x.astype(np.float64)[idx].reshape(T, -1)
+        for l in layers:
+            if l[0] == "mul":
+                h = h * l[1].astype(np.float64)
+            elif l[0] == "linear":
+                h = h @ l[1].astype(np.float64).T + l[2]
+            elif l[0] == "relu":
+                h = np.maximum(h, 0)
+            elif l[0] == "normalize":
+                h = h * np.sqrt(h.shape[1] / np.sum(h * h, axis=1, keepdims=True))
+            else:
+                e = np.exp(h - h.max(1, keepdims=True))
+                h = e / e.sum(1, keepdims=True)
+        return np.log(np.maximum(h, 1e-20)) - np.log(prior.astype(np.float64))
+    assert np.max(np.abs(got - forward64(feats))) < 2e-3
+
+    # a MUL that is not next to a linear layer cannot be folded
+    bad = [base[0], base[1], ("mul", np.ones(96, np.float32))] + base[2:]
+    conf2 = formats.write_model_dir(str(tmp_path), "mul2", bad, prior, 5, 5, list(range(24)),
+                                    cmvn_stats=golden["cmvn_stats"])
     with pytest.raises(pk.PkbError) as e:
-        pk.AcousticModel(ctx).Read(conf)
-    assert e.value.code == 3 and "unexpected layer type: 5" in str(e.value)
+        pk.AcousticModel(ctx).Read(conf2)
+    assert e.value.code == 5
+    with pytest.raises(ValueError):
+        formats.fold_mul_layers(bad)
 
 
 def test_lazy_decodable_matches_eager_bitwise(ctx, golden, toy_conf):

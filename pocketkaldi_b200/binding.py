@@ -369,7 +369,11 @@ class AcousticModel:
         return self
 
     def from_layers(self, layers, prior, left, right, tid2pdf=None):
-        """layers: as pocketkaldi_b200.formats.read_nnet returns them."""
+        """layers: as pocketkaldi_b200.formats.read_nnet returns them (MUL layers are folded
+        the way the file loader folds them)."""
+        if any(l[0] == "mul" for l in layers):
+            from .formats import fold_mul_layers
+            layers = fold_mul_layers(layers)
         names = {"linear": 0, "relu": 1, "normalize": 2, "softmax": 3}
         types = np.array([names[l[0]] for l in layers], np.int32)
         Ws = [_f32(l[1]) for l in layers if l[0] == "linear"]

@@ -43,8 +43,14 @@ constexpr int kMainThreads = 128;   // warps 0-3: TMA producer, MMA issuer, TMEM
 #ifndef PKB_HID_TEAMS
 #define PKB_HID_TEAMS 1
 #endif
-constexpr int epi_teams(bool final, int planes) { return final ? 2 : (planes == 1 ? PKB_HID_TEAMS : 1); }
-constexpr int team_warps(bool final, int planes) { return (final || planes == 1) ? 8 : 4; }
+// PKB_FINAL_TEAMS=1 (one team of 16 warps, four column quarters per lane quadrant) is correct
+// but 6-14 % slower than two teams: pass 2 is bound by the turnaround of each warp's single TMA
+// staging tile and the exchange latency, which only another team's work can cover.
+#ifndef PKB_FINAL_TEAMS
+#define PKB_FINAL_TEAMS 2
+#endif
+constexpr int epi_teams(bool final, int planes) { return final ? PKB_FINAL_TEAMS : (planes == 1 ? PKB_HID_TEAMS : 1); }
+constexpr int team_warps(bool final, int planes) { return final ? 16 / PKB_FINAL_TEAMS : (planes == 1 ? 8 : 4); }
 constexpr int epi_warps(bool final, int planes) { return epi_teams(final, planes) * team_warps(final, planes); }
 constexpr int num_threads(bool final, int planes) { return kMainThreads + 32 * epi_warps(final, planes); }
 constexpr int kMaxStages = 8;
@@ -340,7 +346,7 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool 
   L.stage_bytes = planes * (L.a_plane + L.w_plane);
   // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
   // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch per team
-  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 2 * 128 * 8 : epi_warps(false, planes) * planes * 4096;
+  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 3 * 128 * 8 : epi_warps(false, planes) * planes * 4096;
   uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */ - L.epi_bytes;
   L.stages = avail / L.stage_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
@@ -648,8 +654,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       } else {
         // ---- pass 1 (softmax only): per-row (max, sum exp) over this warp's half of the
         //      tile's columns, exchanged with the warps / CTAs that own the other columns
-        constexpr int kChunks = BN / 64;  // 32-column chunks per epilogue warp
-        const int cbase = chalf * (BN / 2);
+        constexpr int kChunks = BN / 32 / kHalves;  // 32-column chunks per epilogue warp
+        const int cbase = chalf * (BN / kHalves);
         const float kLog2e = 1.4426950408889634f;
         float lse = 0.0f;
         if (p.final_mode != 0) {
@@ -691,16 +697,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           //     (max, sum) per row and column tile, row-fastest so that every warp-wide access
           //     to the exchange buffer is one contiguous 256-byte segment
           const int rit = q * 32 + lane;  // row inside the tile
-          float2 *s_half = reinterpret_cast<float2 *>(s_lp + BN) + team * kBlockM;
-          if (chalf == 1) s_half[rit] = make_float2(run_max, run_sum);
+          // (kTeams * (kHalves - 1) == 2 or 3 scratch planes of 128 rows)
+          float2 *s_half = reinterpret_cast<float2 *>(s_lp + BN) + team * (kHalves - 1) * kBlockM;
+          if (chalf != 0) s_half[(chalf - 1) * kBlockM + rit] = make_float2(run_max, run_sum);
           if (dbg_on) tk2 = clock64();
           named_bar_sync(1 + team, kTeamThreads);
           float2 *xbase = p.lse_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
           if (chalf == 0) {
-            const float2 o = s_half[rit];
-            const float nm = fmaxf(run_max, o.x);
-            const float sm = run_sum * exp2f_fast((run_max - nm) * kLog2e) +
-                             o.y * exp2f_fast((o.x - nm) * kLog2e);
+            float nm = run_max, sm = run_sum;
+#pragma unroll
+            for (int h = 0; h < kHalves - 1; ++h) {
+              const float2 o = s_half[h * kBlockM + rit];
+              const float m2 = fmaxf(nm, o.x);
+              sm = sm * exp2f_fast((nm - m2) * kLog2e) + o.y * exp2f_fast((o.x - m2) * kLog2e);
+              nm = m2;
+            }
             __stcg(&xbase[n_blk * kBlockM + rit], make_float2(nm, sm));
           }
           named_bar_sync(1 + team, kTeamThreads);

@@ -479,7 +479,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         if (p.dbg != nullptr) tw0 = clock64();
         mbar_wait<32>(&tempty[as], aph ^ 1);
         tc_fence_after();
-        if (p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 8 + 6] += clock64() - tw0;
+        if (p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 16 + 6] += clock64() - tw0;
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           if (p.dbg != nullptr) tw0 = clock64();
@@ -509,7 +509,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           if (++s == S) { s = 0; ph ^= 1; }
         }
         umma_commit<CG>(&tfull[as]);  // accumulator complete
-        if (p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 8 + 7] += tw_full;
+        if (p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 16 + 7] += tw_full;
       }
     }
   } else if (warp >= 4) {
@@ -643,7 +643,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           p.out_sumsq[(static_cast<size_t>(row) * p.n_tiles_n + n_blk) * kHalves + chalf] = sumsq;
         if (dbg_on) {
           const long long tk5 = clock64();
-          long long *d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
+          long long *d = p.dbg + static_cast<size_t>(blockIdx.x) * 16;
           d[0] += tk1 - tk0;        // wait for the accumulator
           d[1] += tk3;              // TMEM loads
           d[2] += tk4;              // staged global stores
@@ -753,8 +753,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           const int nvalid = p.N_valid - col0;
           if (nvalid <= 0) break;
           uint32_t v[32];
+          long long q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+          if (dbg_on) q0 = clock64();
           tmem_ld32(taddr + cbase + c * 32, v);
           tmem_ld_wait();
+          if (dbg_on) q1 = clock64();
           float z[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -780,8 +783,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             }
           }
           if (vec_ok) {
+            if (dbg_on) q2 = clock64();
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
+            if (dbg_on) q3 = clock64();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               st_shared_v4(stg_w + ((j ^ (lane & 7)) << 4), __float_as_uint(z[4 * j]),
@@ -792,6 +797,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             if (lane == 0) {
               tma_store_2d(&tm_out, smem_u32(stg), col0, wrow0);
               tma_store_commit();
+            }
+            if (dbg_on) {
+              long long *d = p.dbg + static_cast<size_t>(blockIdx.x) * 16;
+              d[8] += q1 - q0;             // pass 2: TMEM load
+              d[9] += q2 - q1;             // pass 2: math
+              d[10] += q3 - q2;            // pass 2: wait for the staging tile (previous TMA store)
+              d[11] += clock64() - q3;     // pass 2: staging writes, proxy fence, TMA issue
             }
           } else if (row_ok) {
             float *dst = p.out_f32 + static_cast<size_t>(row) * p.ld_f32 + col0;
@@ -807,7 +819,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
         if (dbg_on) {
           const long long tk5 = clock64();
-          long long *d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
+          long long *d = p.dbg + static_cast<size_t>(blockIdx.x) * 16;
           d[0] += tk1 - tk0;  // wait for the accumulator
           d[1] += tk2 - tk1;  // pass 1
           d[2] += tk3 - tk2;  // publish + peer wait
@@ -873,8 +885,8 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
   static const bool dbg_env = getenv("PKB_GEMM_DEBUG") != nullptr;
   long long *dbg = nullptr;
   if (dbg_env) {
-    cudaMalloc(&dbg, sizeof(long long) * 8 * grid);
-    cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * grid, c->stream);
+    cudaMalloc(&dbg, sizeof(long long) * 16 * grid);
+    cudaMemsetAsync(dbg, 0, sizeof(long long) * 16 * grid, c->stream);
   }
   pp.dbg = dbg;
   {
@@ -925,17 +937,17 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
   PKB_CUDA(cudaGetLastError());
   }
   if (dbg) {
-    std::vector<long long> h(8 * grid);
+    std::vector<long long> h(16 * grid);
     cudaStreamSynchronize(c->stream);
-    cudaMemcpy(h.data(), dbg, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h.data(), dbg, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost);
     cudaFree(dbg);
-    double s[8] = {0};
+    double s[16] = {0};
     for (int b = 0; b < grid; ++b)
-      for (int k = 0; k < 8; ++k) s[k] += h[8 * b + k];
+      for (int k = 0; k < 16; ++k) s[k] += h[16 * b + k];
     const double n = s[5] > 0 ? s[5] : 1;
     if (FINAL)
-      fprintf(stderr, "[pkb gemm final] tiles/cta=%.0f cycles/tile: wait_acc=%.0f pass1=%.0f sync=%.0f combine=%.0f pass2=%.0f | mma: wait_tmem=%.0f wait_smem=%.0f\n",
-              n / grid, s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n, s[6] / n, s[7] / n);
+      fprintf(stderr, "[pkb gemm final] tiles/cta=%.0f cycles/tile: wait_acc=%.0f pass1=%.0f sync=%.0f combine=%.0f pass2=%.0f (tmem_ld=%.0f math=%.0f stage_wait=%.0f stage_write=%.0f) | mma: wait_tmem=%.0f wait_smem=%.0f\n",
+              n / grid, s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n, s[8] / n, s[9] / n, s[10] / n, s[11] / n, s[6] / n, s[7] / n);
     else
       fprintf(stderr, "[pkb gemm kb=%d] tiles/cta=%.0f cycles/tile: wait_acc=%.0f tmem_ld=%.0f math=%.0f stores=%.0f epilogue=%.0f | mma: wait_tmem=%.0f wait_smem=%.0f\n",
               p.num_kb, n / grid, s[0] / n, s[1] / n, s[4] / n, s[2] / n, s[3] / n, s[6] / n * CG, s[7] / n * CG);

@@ -50,7 +50,7 @@ constexpr int kMainThreads = 128;   // warps 0-3: TMA producer, MMA issuer, TMEM
 #define PKB_FINAL_TEAMS 2
 #endif
 constexpr int epi_teams(bool final, int planes) { return final ? PKB_FINAL_TEAMS : (planes == 1 ? PKB_HID_TEAMS : 1); }
-constexpr int team_warps(bool final, int planes) { return final ? 16 / PKB_FINAL_TEAMS : (planes == 1 ? 8 : 4); }
+constexpr int team_warps(bool final, int planes) { return final ? 16 / PKB_FINAL_TEAMS : (planes == 1 ? PKB_HID_WARPS : 4); }
 constexpr int epi_warps(bool final, int planes) { return epi_teams(final, planes) * team_warps(final, planes); }
 constexpr int num_threads(bool final, int planes) { return kMainThreads + 32 * epi_warps(final, planes); }
 constexpr int kMaxStages = 8;

@@ -77,7 +77,11 @@ int make_output_map(CUtensorMap *map, const float *base, uint64_t cols, uint64_t
 
 int gemm_max_smem_bytes(int block_n, int planes);
 
+// Epilogue warps of a single-plane hidden stage: 8 (two per TMEM lane quadrant) or 4.
+#ifndef PKB_HID_WARPS
+#define PKB_HID_WARPS 8
+#endif
 // Sum-of-squares partials one hidden tile writes per row (= epilogue warps per lane quadrant).
-inline int sumsq_parts(int planes) { return planes == 1 ? 2 : 1; }
+inline int sumsq_parts(int planes) { return planes == 1 ? PKB_HID_WARPS / 4 : 1; }
 
 }  // namespace pkb

@@ -894,7 +894,8 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
   if (FINAL && p.final_mode != 0) {
     // the column tiles of a row block exchange softmax partials through global memory and wait
     // for each other: a cooperative launch guarantees that all CTAs are co-resident
-    PKB_CUDA(cudaMemsetAsync(p.tile_done, 0, sizeof(int) * ((p.M + kBlockM - 1) / kBlockM), c->stream));
+    // (+1: a CTA pair may work on one row block past the end of the matrix)
+    PKB_CUDA(cudaMemsetAsync(p.tile_done, 0, sizeof(int) * ((p.M + kBlockM - 1) / kBlockM + 1), c->stream));
     CUtensorMap m0 = *a_hi, m1 = *a_lo, m2 = *w_hi, m3 = *w_lo;
     void *args[] = {&m0, &m1, &m2, &m3, &out_map, &pp};
     if (CG == 1) {

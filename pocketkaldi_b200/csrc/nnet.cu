@@ -306,7 +306,7 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
   const Stage &last = am->stages.back();
   PKB_TRY(ws->lse_part.ensure(static_cast<size_t>((rows + kBlockM - 1) / kBlockM) * kBlockM *
                               2 * (last.n_pad / last.block_n) * sizeof(float2)));
-  PKB_TRY(ws->tile_done.ensure(sizeof(int) * static_cast<size_t>((rows + kBlockM - 1) / kBlockM)));
+  PKB_TRY(ws->tile_done.ensure(sizeof(int) * (static_cast<size_t>((rows + kBlockM - 1) / kBlockM) + 1)));
   return PKB_OK;
 }
 

@@ -9,11 +9,13 @@
 // in their on-disk [out][in] layout (K-major for both operands), so the transpose
 // of LinearLayer::LinearLayer (src/nnet.cc:16-17) disappears.
 //
-// CTA = 8 warps: warp 0 lane 0 TMA producer, warp 1 lane 0 MMA issuer, warp 2 TMEM
-// allocator, warps 4-7 epilogue (TMEM lane quadrant = warp % 4). Three pipelines:
-// smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <->
-// epilogue), static persistent tile loop with N fastest so that co-resident CTAs
-// share the activation tile in L2.
+// CTA: warp 0 lane 0 TMA producer, warp 1 lane 0 MMA issuer, warp 2 TMEM allocator, warps 4+
+// epilogue (TMEM lane quadrant = warp % 4; 8 warps for single-plane hidden stages, 4 in BF16X3,
+// 16 = two teams of 8 for the output stage). Three pipelines: smem full/empty ring (TMA <-> MMA),
+// TMEM full/empty double buffer (MMA <-> epilogue), static persistent tile loop with N fastest
+// so that co-resident CTAs share the activation tile in L2 (output stage with softmax: grouped
+// schedule, see get_tile). Hidden stages (and the BF16X3 output stage) run as CTA pairs
+// (cta_group::2): one 256-row MMA tile per cluster of two, each CTA loading half of the W tile.
 //
 // BF16X3: every operand is carried as two BF16 planes (hi, lo = bf16(x - hi)) and
 // each K step issues hi*hi + lo*hi + hi*lo into the same accumulator, which brings

@@ -65,6 +65,8 @@ const char *pkb_version(void);
  * set-up of Fbank::Fbank, src/fbank.cc:258-265, and pk_srfft_init,
  * src/srfft.cc:343-356). */
 int pkb_create(int device, pkb_ctx_t **ctx);
+/* Every object created on a context (models, batches, streams, events) must be destroyed
+ * before the context itself. */
 void pkb_destroy(pkb_ctx_t *ctx);
 /* Blocks until all work queued on the context's stream has finished. */
 int pkb_sync(pkb_ctx_t *ctx);

@@ -56,6 +56,13 @@ constexpr int team_warps(bool final, int planes) { return final ? 16 / PKB_FINAL
 constexpr int epi_warps(bool final, int planes) { return epi_teams(final, planes) * team_warps(final, planes); }
 constexpr int num_threads(bool final, int planes) { return kMainThreads + 32 * epi_warps(final, planes); }
 constexpr int kMaxStages = 8;
+// clock64 probes of the pipeline phases (PKB_GEMM_DEBUG=1 prints them). Compiled in only with
+// -DPKB_GEMM_PROBES: even switched off at run time they cost the hidden stages cycles.
+#ifdef PKB_GEMM_PROBES
+constexpr bool kProbes = true;
+#else
+constexpr bool kProbes = false;
+#endif
 constexpr uint32_t kSmemBudget = 227 * 1024;
 
 // ---------------------------------------------------------------- PTX helpers
@@ -478,16 +485,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       for (int it = 0; get_tile<CG>(p, it, cta_rank, m_blk, n_blk); ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
         long long tw0 = 0, tw_full = 0;
-        if (p.dbg != nullptr) tw0 = clock64();
+        if (kProbes && p.dbg != nullptr) tw0 = clock64();
         mbar_wait<32>(&tempty[as], aph ^ 1);
         tc_fence_after();
-        if (p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 16 + 6] += clock64() - tw0;
+        if (kProbes && p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 16 + 6] += clock64() - tw0;
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          if (p.dbg != nullptr) tw0 = clock64();
+          if (kProbes && p.dbg != nullptr) tw0 = clock64();
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          if (p.dbg != nullptr) tw_full += clock64() - tw0;
+          if (kProbes && p.dbg != nullptr) tw_full += clock64() - tw0;
           const uint32_t sa = smem_u32(smem + s * L.stage_bytes);
           const uint32_t sw = sa + PLANES * L.a_plane;
           const uint64_t a_hi = make_smem_desc(sa);
@@ -511,7 +518,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           if (++s == S) { s = 0; ph ^= 1; }
         }
         umma_commit<CG>(&tfull[as]);  // accumulator complete
-        if (p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 16 + 7] += tw_full;
+        if (kProbes && p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 16 + 7] += tw_full;
       }
     }
   } else if (warp >= 4) {
@@ -561,7 +568,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       }
 
       long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tkm = 0;
-      const bool dbg_on = p.dbg != nullptr && warp == 4 && lane == 0;  // team 0
+      const bool dbg_on = kProbes && p.dbg != nullptr && warp == 4 && lane == 0;  // team 0
       if (dbg_on) tk0 = clock64();
       mbar_wait<32>(&tfull[as], aph);
       tc_fence_after();
@@ -884,7 +891,7 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
     pp.group_sched = 1;
     grid = CG * std::min(max_units / p.n_tiles_n, m_units) * p.n_tiles_n;
   }
-  static const bool dbg_env = getenv("PKB_GEMM_DEBUG") != nullptr;
+  static const bool dbg_env = kProbes && getenv("PKB_GEMM_DEBUG") != nullptr;
   long long *dbg = nullptr;
   if (dbg_env) {
     cudaMalloc(&dbg, sizeof(long long) * 16 * grid);

@@ -273,7 +273,7 @@ def run_gpu_arm(args, cfg):
     if cfg["nnet"]:
         achieved = flops_per_frame(cfg) * frames * args.steps / (gemm_ms * 1e-3) / 1e12
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1e_gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r1f_gemm_traffic.json")
         if args.config == "3" and os.path.exists(tpath):
             # dram__bytes_read+write of the 7 GEMM launches of one step (ncu --set full at 512
             # utterances, linear in frames), averaged per launch like `achieved`

@@ -72,7 +72,7 @@ def make_layers(cfg, seed=0):
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_power_cap,power.limit")
 
     def __init__(self, index):
         self.path = tempfile.mktemp(prefix="pkb_clocks_", suffix=".csv")
@@ -94,7 +94,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, lim, reasons = [], [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in open(self.path):
@@ -106,6 +106,14 @@ class ClockSampler:
                     mx.append(float(f[1]))
                 except ValueError:
                     continue
+                try:
+                    pw.append(float(f[2]))
+                except ValueError:
+                    pw.append(0.0)
+                try:
+                    lim.append(float(f[7]))
+                except (ValueError, IndexError):
+                    pass
                 for n, v in zip(names, f[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
@@ -113,10 +121,14 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            # median of the samples taken under load (upper half)
-            top = sorted(sm)[len(sm) // 2:]
-            out["sm_mhz"] = float(np.median(top))
+            # samples taken under load = those drawing at least 70 % of the highest power seen
+            # (under a power cap the loaded clock is the LOWER one)
+            loaded = [c for c, w in zip(sm, pw) if w >= 0.7 * max(pw)] or sm
+            out["sm_mhz"] = float(np.median(loaded))
             out["sm_max_mhz"] = float(max(mx))
+            out["power_w"] = float(np.median([w for w in pw if w >= 0.7 * max(pw)] or pw))
+            if lim:
+                out["power_limit_w"] = float(max(lim))
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
         return out

@@ -282,6 +282,7 @@ def run_gpu_arm(args, cfg):
     gemm_ms = prof["gemm"][1] + prof["gemm_final"][1]
     fb_ms = prof["fbank"][1] + prof["cmvn"][1]
     front_gbs = 480.0 * frames * args.steps / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else None
+    cmvn_gbs = 320.0 * frames * args.steps / (prof["cmvn"][1] * 1e-3) / 1e9 if prof["cmvn"][1] > 0 else None
     if cfg["nnet"]:
         achieved = flops_per_frame(cfg) * frames * args.steps / (gemm_ms * 1e-3) / 1e12
         traffic = None
@@ -351,7 +352,10 @@ def run_gpu_arm(args, cfg):
                                   "achieved": front_gbs, "peak": peaks["hbm"], "unit": "GB/s",
                                   "frac": (front_gbs / peaks["hbm"]) if front_gbs else None,
                                   "fbank_ms_per_step": prof["fbank"][1] / args.steps,
-                                  "cmvn_ms_per_step": prof["cmvn"][1] / args.steps},
+                                  "cmvn_ms_per_step": prof["cmvn"][1] / args.steps,
+                                  # the stand-alone CMVN kernel is the HBM-bound one (320 B/frame)
+                                  "cmvn_gbs": cmvn_gbs,
+                                  "cmvn_frac": (cmvn_gbs / peaks["hbm"]) if cmvn_gbs else None},
             "kernel_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()},
             "cpu_baseline": cpu,
             "e2e": e2e,

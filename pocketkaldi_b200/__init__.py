@@ -32,6 +32,7 @@ from .binding import (  # noqa: F401
     STAGE_CMVN,
     STAGE_NNET,
     STAGE_ALL,
+    STAGE_NO_FEATS,
     BUF_PCM,
     BUF_RAW,
     BUF_FEATS,

@@ -425,7 +425,7 @@ int pkb_am_compute(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t
   PKB_TRY(pkb::copy_rows_compact(c, loglik_out, am->out_f32.as<float>(), m, pad_off, am->num_pdfs, 0,
                                  m.total_frames));
   PKB_CUDA(cudaStreamSynchronize(c->stream));
-  return PKB_OK;
+  return pkb::check_device_error(c, "pkb_am_compute");
 }
 
 struct pkb_event {
@@ -542,7 +542,7 @@ int pkb_nnet_propagate(pkb_ctx_t *c, pkb_am_t *am, const float *in_host, int row
   PKB_TRY(pkb::nnet_forward(am, &ws, in, &am->stages[0], mode, 1.0f, am->out_f32.as<float>()));
   PKB_CUDA(cudaMemcpyAsync(out, am->out_f32.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   PKB_CUDA(cudaStreamSynchronize(c->stream));
-  return PKB_OK;
+  return pkb::check_device_error(c, "pkb_nnet_propagate");
 }
 
 // ---------------------------------------------------------------- batch pipeline
@@ -643,6 +643,7 @@ int pkb_batch_set_pcm_i16(pkb_batch_t *b, const int16_t *pcm) {
   PKB_REQUIRE(b, "pkb_batch_set_pcm_i16: batch is NULL");
   if (b->meta.total_samples == 0) return PKB_OK;
   PKB_REQUIRE(pcm, "pkb_batch_set_pcm_i16: pcm is NULL");
+  PKB_CUDA(cudaSetDevice(b->c->device));
   PKB_CUDA(cudaMemcpyAsync(b->pcm.p, pcm, static_cast<size_t>(b->meta.total_samples) * 2,
                            cudaMemcpyHostToDevice, b->c->stream));
   return PKB_OK;
@@ -650,17 +651,20 @@ int pkb_batch_set_pcm_i16(pkb_batch_t *b, const int16_t *pcm) {
 
 int pkb_batch_synth_pcm(pkb_batch_t *b, uint64_t seed, uint64_t first_utt_id) {
   PKB_REQUIRE(b, "pkb_batch_synth_pcm: batch is NULL");
+  PKB_CUDA(cudaSetDevice(b->c->device));
   return pkb::launch_synth_pcm(b->c, b->pcm.as<int16_t>(), b->meta, seed, first_utt_id);
 }
 
 int pkb_batch_run(pkb_batch_t *b, int stages) {
   PKB_REQUIRE(b, "pkb_batch_run: batch is NULL");
   Ctx *c = b->c;
+  PKB_CUDA(cudaSetDevice(c->device));
   if (stages & PKB_STAGE_FBANK)
     PKB_TRY(pkb::launch_fbank_i16(c, b->pcm.as<int16_t>(), b->meta, b->raw.as<float>()));
   if (stages & PKB_STAGE_CMVN) {
     PKB_TRY(pkb::prepare_cmvn_tables(c, b->global_stats));
-    PKB_TRY(pkb::launch_cmvn(c, b->raw.as<float>(), b->meta, b->feats.as<float>(),
+    const bool skip_f32 = (stages & PKB_STAGE_NO_FEATS) && b->am;
+    PKB_TRY(pkb::launch_cmvn(c, b->raw.as<float>(), b->meta, skip_f32 ? nullptr : b->feats.as<float>(),
                              b->am ? &b->planes : nullptr));
   }
   if (stages & PKB_STAGE_NNET) {
@@ -717,6 +721,7 @@ int pkb_batch_get_rows(pkb_batch_t *b, int which, int64_t row0, int64_t n_rows, 
               (long long)(row0 + n_rows), (long long)rows);
   if (n_rows == 0) return PKB_OK;
   PKB_REQUIRE(host_dst, "pkb_batch_get_rows: host_dst is NULL");
+  PKB_CUDA(cudaSetDevice(b->c->device));
   if (which == PKB_BUF_LOGLIK)  // stored with padded rows: compact per utterance on the way out
     return pkb::copy_rows_compact(b->c, host_dst, b->loglik.as<float>(), b->meta, b->pad_off,
                                   b->am->num_pdfs, row0, n_rows);
@@ -737,6 +742,7 @@ int pkb_batch_get(pkb_batch_t *b, int which, void *host_dst) {
 int pkb_batch_checksum(pkb_batch_t *b, int which, double *sum_out) {
   PKB_REQUIRE(b && sum_out, "pkb_batch_checksum: NULL argument");
   PKB_REQUIRE(which != PKB_BUF_PCM, "pkb_batch_checksum: float buffers only");
+  PKB_CUDA(cudaSetDevice(b->c->device));
   char *ptr = nullptr;
   size_t row_bytes = 0;
   int64_t rows = 0;
@@ -749,7 +755,7 @@ int pkb_batch_checksum(pkb_batch_t *b, int which, double *sum_out) {
     PKB_TRY(pkb::launch_checksum(b->c, reinterpret_cast<const float *>(ptr), n, b->sum.as<double>()));
   PKB_CUDA(cudaMemcpyAsync(sum_out, b->sum.p, sizeof(double), cudaMemcpyDeviceToHost, b->c->stream));
   PKB_CUDA(cudaStreamSynchronize(b->c->stream));
-  return PKB_OK;
+  return pkb::check_device_error(b->c, "pkb_batch_checksum");
 }
 
 // ---------------------------------------------------------------- fused host path
@@ -772,6 +778,8 @@ int pkb_pcm_to_loglik_i16(pkb_ctx_t *c, pkb_am_t *am, const int16_t *pcm,
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
       pkb::set_error("pkb_pcm_to_loglik_i16: %s", cudaGetErrorString(cudaGetLastError()));
       rc = PKB_ERR_CUDA;
+    } else {
+      rc = pkb::check_device_error(c, "pkb_pcm_to_loglik_i16");
     }
   } while (0);
   pkb_batch_destroy(b);

@@ -14,6 +14,7 @@
 // tabulated on the host with the reference's double/float arithmetic.
 
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -34,56 +35,116 @@ struct CmvnChain {
   float gd;               // global stat of this dim
 };
 
+// RN32(a + b + c) for binary32 a, b, c without widening: Boldo & Melquiond's three-term sum
+// (two TwoSums, then the two error terms added with rounding to odd, emulated with a
+// round-down / round-up pair). Exact for any inputs short of overflow / underflow.
+__device__ __forceinline__ float sum3_rn(float a, float b, float c) {
+  const float uh = __fadd_rn(b, c);
+  const float ub = __fsub_rn(uh, b);
+  const float ul = __fadd_rn(__fsub_rn(b, __fsub_rn(uh, ub)), __fsub_rn(c, ub));
+  const float th = __fadd_rn(a, uh);
+  const float tb = __fsub_rn(th, a);
+  const float tl = __fadd_rn(__fsub_rn(a, __fsub_rn(th, tb)), __fsub_rn(uh, tb));
+  const float vd = __fadd_rd(tl, ul), vu = __fadd_ru(tl, ul);
+  const float v = (vd == vu || (__float_as_uint(vd) & 1u)) ? vd : vu;
+  return __fadd_rn(th, v);
+}
+
+// The reference forms double(stat) + x - x_old and rounds to float once per frame
+// (src/cmvn.cc:35-71). When every value that entered the chain is 0 or has 2^-6 <= |v| < 2^12, all
+// three terms are multiples of 2^-29 below 2^23, both double additions are exact, and the
+// step is RN32 of the exact three-term sum -- which sum3_rn delivers on the FP32 pipe (the FP64
+// pipe of this part issues one warp instruction per 16 cycles). A chain that has seen a value
+// outside that range (digital silence gives log(FLT_EPSILON) = -15.9, which is fine; energies
+// within 1.6 % of 1.0 or non-finite values are not) stays on the FP64 path.
+__device__ __forceinline__ bool cmvn_out_of_range(float x) {
+  const uint32_t u = __float_as_uint(x) & 0x7fffffffu;
+  return u != 0u && (u - 0x3C800000u) >= (0x45800000u - 0x3C800000u);
+}
+
 // One frame of the recurrence (ComputeStats -> SmoothStats -> Apply, src/cmvn.cc:35-101).
 //   kSub:   the window is full, the frame 600 steps back leaves the sum (t >= 600)
 //   kAlpha: fewer than 600 frames seen, the global stats are blended in (t < 599)
-template <bool kSub, bool kAlpha, int kPlanes, bool kFp16>
-__device__ __forceinline__ void cmvn_frame(const CmvnChain &c, int t, float x, float xold, float &stat,
-                                           const float *s_alpha, const float *s_scale, float scale_full) {
-  double acc = static_cast<double>(stat) + static_cast<double>(x);
-  if (kSub) acc += -1.0 * static_cast<double>(xold);
-  stat = static_cast<float>(acc);
+//   kF64:   widen like the reference (only needed for kSub, see above)
+template <bool kSub, bool kAlpha, bool kF64, int kPlanes, bool kFp16, bool kOut>
+__device__ __forceinline__ void cmvn_frame(const CmvnChain &c, int t, int i, float x, float xold, float &stat,
+                                           float alpha, float sc) {
+  // t = first frame of the group, i = compile-time index inside it: every address below is one
+  // group base plus an immediate offset
+  if (!kSub) {
+    // double(stat) + double(x) rounded to float == the float sum: the double sum is exact when
+    // the exponents are within 29 of each other and cannot reach a rounding boundary otherwise
+    stat = __fadd_rn(stat, x);
+  } else if (kF64) {
+    double acc = static_cast<double>(stat) + static_cast<double>(x);
+    acc += -1.0 * static_cast<double>(xold);
+    stat = static_cast<float>(acc);
+  } else {
+    stat = sum3_rn(stat, x, -xold);
+  }
   float s = stat;
-  if (kAlpha) s = __fadd_rn(s, __fmul_rn(s_alpha[t], c.gd));
-  const float sc = kSub ? scale_full : s_scale[t];
+  if (kAlpha) s = __fadd_rn(s, __fmul_rn(alpha, c.gd));
   const float v = __fadd_rn(x, __fmul_rn(-sc, s));
-  if (c.y) c.y[static_cast<int64_t>(t) * kMel] = v;
+  if (kOut) (c.y + static_cast<int64_t>(t) * kMel)[i * kMel] = v;
   if (kPlanes >= 1) {
+    // plane rows are kMel elements apart (feat_dim_pad == kMel: 40 is a multiple of 8)
     const __nv_bfloat16 h = operand_bits(v, kFp16);
-    c.ph[static_cast<int64_t>(t) * c.dim_pad] = h;
-    if (kPlanes == 2) c.pl[static_cast<int64_t>(t) * c.dim_pad] = operand_bits(v - operand_value(h, kFp16), kFp16);
+    (c.ph + static_cast<int64_t>(t) * kMel)[i * kMel] = h;
+    if (kPlanes == 2)
+      (c.pl + static_cast<int64_t>(t) * kMel)[i * kMel] = operand_bits(v - operand_value(h, kFp16), kFp16);
   }
 }
 
-// Frames [tb, te) of one phase. The chain is ~4 dependent operations per frame; what has to be
+// Frames [tb, te) of one phase. The chain is a few dependent operations per frame; what has to be
 // hidden is the load latency, so the loads of the next group of kCmvnUnroll frames are issued
 // before the current group is consumed (two register sets). Whole groups run without
-// per-frame bounds checks; the last, partial group is predicated.
-template <bool kSub, bool kAlpha, int kPlanes, bool kFp16>
-__device__ __forceinline__ void cmvn_phase(const CmvnChain &c, int tb, int te, float &stat,
+// per-frame bounds checks; the last, partial group is predicated. `wide` is the chain's sticky
+// "a value outside the exact-FP32 range was seen" flag.
+template <bool kSub, bool kAlpha, int kPlanes, bool kFp16, bool kOut>
+__device__ __forceinline__ void cmvn_phase(const CmvnChain &c, int tb, int te, float &stat, bool &wide,
                                            const float *s_alpha, const float *s_scale, float scale_full) {
   if (tb >= te) return;
   float xa[kCmvnUnroll], pa[kCmvnUnroll], xb[kCmvnUnroll], pb[kCmvnUnroll];
   auto load = [&](int t0, float (&xv)[kCmvnUnroll], float (&xp)[kCmvnUnroll]) {
     const bool whole = t0 + kCmvnUnroll <= te;
+    const float *px = c.x + static_cast<int64_t>(t0) * kMel;
 #pragma unroll
     for (int i = 0; i < kCmvnUnroll; ++i) {
-      const int t = t0 + i;
-      const bool ok = whole || t < te;
-      xv[i] = ok ? c.x[static_cast<int64_t>(t) * kMel] : 0.0f;
-      xp[i] = (kSub && ok) ? c.x[static_cast<int64_t>(t - kCmvnWindow) * kMel] : 0.0f;
+      const bool ok = whole || t0 + i < te;
+      xv[i] = ok ? px[i * kMel] : 0.0f;
+      xp[i] = (kSub && ok) ? px[(i - kCmvnWindow) * kMel] : 0.0f;
     }
   };
   auto consume = [&](int t0, const float (&xv)[kCmvnUnroll], const float (&xp)[kCmvnUnroll]) {
-    if (t0 + kCmvnUnroll <= te) {
+    // out-of-range values of the group make the chain wide before they are used; every x_old was
+    // an x of this chain 600 frames earlier, so it has been checked already
+    bool w = wide;
+#pragma unroll
+    for (int i = 0; i < kCmvnUnroll; ++i) w = w || cmvn_out_of_range(xv[i]);
+    wide = w;
+    const bool whole = t0 + kCmvnUnroll <= te;
+    float al[kCmvnUnroll], sc[kCmvnUnroll];
+#pragma unroll
+    for (int i = 0; i < kCmvnUnroll; ++i) {
+      // the tables have 600 entries and the phases that use them end at t = 599 / 600
+      const int ti = min(t0 + i, kCmvnWindow - 1);
+      al[i] = kAlpha ? s_alpha[ti] : 0.0f;
+      sc[i] = kSub ? scale_full : s_scale[ti];
+    }
+    if (kSub && w) {
 #pragma unroll
       for (int i = 0; i < kCmvnUnroll; ++i)
-        cmvn_frame<kSub, kAlpha, kPlanes, kFp16>(c, t0 + i, xv[i], xp[i], stat, s_alpha, s_scale, scale_full);
+        if (whole || t0 + i < te)
+          cmvn_frame<kSub, kAlpha, true, kPlanes, kFp16, kOut>(c, t0, i, xv[i], xp[i], stat, al[i], sc[i]);
+    } else if (whole) {
+#pragma unroll
+      for (int i = 0; i < kCmvnUnroll; ++i)
+        cmvn_frame<kSub, kAlpha, false, kPlanes, kFp16, kOut>(c, t0, i, xv[i], xp[i], stat, al[i], sc[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < kCmvnUnroll; ++i)
         if (t0 + i < te)
-          cmvn_frame<kSub, kAlpha, kPlanes, kFp16>(c, t0 + i, xv[i], xp[i], stat, s_alpha, s_scale, scale_full);
+          cmvn_frame<kSub, kAlpha, false, kPlanes, kFp16, kOut>(c, t0, i, xv[i], xp[i], stat, al[i], sc[i]);
     }
   };
   load(tb, xa, pa);
@@ -95,10 +156,10 @@ __device__ __forceinline__ void cmvn_phase(const CmvnChain &c, int tb, int te, f
   }
 }
 
-// 7 blocks of 160 threads (35 warps) per SM: 56 registers. Measured at 4096 utterances: 433 us
-// (3.8 TB/s) against 465 us with 6 blocks and 560 us with 8 (spills).
-template <int kPlanes, bool kFp16>
-__global__ void __launch_bounds__(160, 7)
+// One thread per chain, up to 160 threads (four utterances) per block; at most 4 blocks per SM
+// (the two prefetch register sets must not spill).
+template <int kPlanes, bool kFp16, bool kOut>
+__global__ void __launch_bounds__(160, 4)
 cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off,
             const int32_t *__restrict__ num_frames, int n_utts,
             const float *__restrict__ tab /* alpha[600], scale[600], global[41] */,
@@ -121,7 +182,7 @@ cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off
   CmvnChain c;
   c.gd = tab[2 * kCmvnWindow + d];
   c.x = raw + frame_off[u] * kMel + d;
-  c.y = out ? out + frame_off[u] * kMel + d : nullptr;
+  c.y = kOut ? out + frame_off[u] * kMel + d : nullptr;
   c.dim_pad = dim_pad;
   c.ph = kPlanes >= 1 ? p_hi + (pad_off[u] + left) * dim_pad + d : nullptr;
   c.pl = kPlanes == 2 ? p_lo + (pad_off[u] + left) * dim_pad + d : nullptr;
@@ -130,10 +191,11 @@ cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off
   // (t < 599), the frame that completes the window (t = 599: no smoothing, nothing leaves yet),
   // and the full sliding window (t >= 600: scale is the constant 1/600)
   float stat = 0.0f;
+  bool wide = false;
   const float scale_full = s_scale[kCmvnWindow - 1];
-  cmvn_phase<false, true, kPlanes, kFp16>(c, 0, min(T, kCmvnWindow - 1), stat, s_alpha, s_scale, scale_full);
-  cmvn_phase<false, false, kPlanes, kFp16>(c, kCmvnWindow - 1, min(T, kCmvnWindow), stat, s_alpha, s_scale, scale_full);
-  cmvn_phase<true, false, kPlanes, kFp16>(c, kCmvnWindow, T, stat, s_alpha, s_scale, scale_full);
+  cmvn_phase<false, true, kPlanes, kFp16, kOut>(c, 0, min(T, kCmvnWindow - 1), stat, wide, s_alpha, s_scale, scale_full);
+  cmvn_phase<false, false, kPlanes, kFp16, kOut>(c, kCmvnWindow - 1, min(T, kCmvnWindow), stat, wide, s_alpha, s_scale, scale_full);
+  cmvn_phase<true, false, kPlanes, kFp16, kOut>(c, kCmvnWindow, T, stat, wide, s_alpha, s_scale, scale_full);
 
   // replicated edge rows of the padded planes (AcousticModel::SpliceFeats clamps at the
   // utterance edges, src/am.cc:65-88): copies of this thread's own first / last element
@@ -232,22 +294,40 @@ int launch_cmvn(Ctx *c, const float *d_raw, const BatchMeta &m, float *d_out,
   if (m.n_utts == 0 || m.total_frames == 0) return PKB_OK;
   PKB_REQUIRE(c->cmvn_valid, "cmvn: tables not prepared");
   const int64_t threads = static_cast<int64_t>(m.n_utts) * kMel;
-  const int block = 160;
+  // a chain is sequential in t, so parallelism is n_utts * 40 threads: small batches run as
+  // single-warp blocks spread over all SM sub-partitions instead of a few 5-warp blocks
+  const int block = threads >= static_cast<int64_t>(c->sm_count) * 4 * 160 ? 160 : 32;
   const int grid = static_cast<int>((threads + block - 1) / block);
+  // PKB_CMVN_BLOCKS_PER_SM=n (tuning knob): caps residency with unused dynamic shared memory
+  static const int max_blocks = getenv("PKB_CMVN_BLOCKS_PER_SM") ? atoi(getenv("PKB_CMVN_BLOCKS_PER_SM")) : 0;
+  const size_t dyn_smem = max_blocks > 0 ? std::max<size_t>(0, (220 * 1024) / max_blocks - 6 * 1024) : 0;
   LaunchScope scope(c, PKB_KERNEL_CMVN);
   __nv_bfloat16 *hi = planes ? planes->hi : nullptr, *lo = planes ? planes->lo : nullptr;
   const int n_planes = hi ? (lo ? 2 : 1) : 0;
   const bool fp16 = planes && planes->fp16;
-#define PKB_CMVN_LAUNCH(PL, FP)                                                                    \
-  cmvn_kernel<PL, FP><<<grid, block, 0, c->stream>>>(                                              \
-      d_raw, m.d_frame_off, m.d_num_frames, m.n_utts, c->cmvn_tab.as<float>(), d_out, hi, lo,      \
-      planes ? planes->d_pad_off : nullptr, planes ? planes->left : 0, planes ? planes->right : 0, \
-      planes ? planes->dim_pad : 0)
-  if (n_planes == 0) PKB_CMVN_LAUNCH(0, false);
+  PKB_REQUIRE(!planes || planes->dim_pad == kMel, "cmvn: operand planes must have a row pitch of %d elements", kMel);
+#define PKB_CMVN_LAUNCH2(PL, FP, OUT)                                                                \
+  do {                                                                                               \
+    if (dyn_smem > 0)                                                                                \
+      cudaFuncSetAttribute(cmvn_kernel<PL, FP, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                           static_cast<int>(dyn_smem));                                              \
+    cmvn_kernel<PL, FP, OUT><<<grid, block, dyn_smem, c->stream>>>(                                  \
+        d_raw, m.d_frame_off, m.d_num_frames, m.n_utts, c->cmvn_tab.as<float>(), d_out, hi, lo,      \
+        planes ? planes->d_pad_off : nullptr, planes ? planes->left : 0, planes ? planes->right : 0, \
+        planes ? planes->dim_pad : 0);                                                               \
+  } while (0)
+#define PKB_CMVN_LAUNCH(PL, FP)                  \
+  do {                                           \
+    if (d_out) PKB_CMVN_LAUNCH2(PL, FP, true);   \
+    else PKB_CMVN_LAUNCH2(PL, FP, false);        \
+  } while (0)
+  PKB_REQUIRE(d_out || n_planes > 0, "cmvn: no output requested");
+  if (n_planes == 0) PKB_CMVN_LAUNCH2(0, false, true);
   else if (n_planes == 1 && !fp16) PKB_CMVN_LAUNCH(1, false);
   else if (n_planes == 1 && fp16) PKB_CMVN_LAUNCH(1, true);
   else if (n_planes == 2 && !fp16) PKB_CMVN_LAUNCH(2, false);
   else PKB_CMVN_LAUNCH(2, true);
+#undef PKB_CMVN_LAUNCH2
 #undef PKB_CMVN_LAUNCH
   PKB_CUDA(cudaGetLastError());
   return PKB_OK;

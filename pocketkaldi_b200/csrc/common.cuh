@@ -88,6 +88,10 @@ struct Ctx {
   bool cmvn_valid = false;
   // scratch for the host-buffer entry points
   DevBuf s_in, s_meta, s_raw, s_out, s_flush;
+  // device -> host error word (mapped pinned memory): a kernel that gives up on a bounded wait
+  // stores a code here instead of trapping, which would poison the whole CUDA context
+  int *err_host = nullptr;
+  int *err_dev = nullptr;
   // timers / profiling
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool profile = false;
@@ -96,6 +100,9 @@ struct Ctx {
   std::vector<ProfSpan> spans;
   std::vector<cudaEvent_t> free_events;
 };
+
+// Reports (and clears) an error word left by a kernel; call after a stream synchronisation.
+int check_device_error(Ctx *c, const char *who);
 
 // RAII launch accounting: counts every launch, and with profiling on brackets
 // it with an event pair on the context stream.

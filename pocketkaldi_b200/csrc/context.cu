@@ -45,6 +45,16 @@ void DevBuf::release() {
   cap = 0;
 }
 
+int check_device_error(Ctx *c, const char *who) {
+  if (c->err_host == nullptr) return PKB_OK;
+  const int code = *static_cast<volatile int *>(c->err_host);
+  if (code == 0) return PKB_OK;
+  *c->err_host = 0;
+  set_error("%s: a kernel gave up waiting for its peer CTAs (code %d: softmax exchange of the "
+            "output layer); the results of this call are invalid", who, code);
+  return PKB_ERR_CUDA;
+}
+
 LaunchScope::LaunchScope(Ctx *ctx, int cls) : c(ctx), timed(false) {
   span.cls = cls;
   c->launches[cls]++;
@@ -193,6 +203,13 @@ int pkb_create(int device, pkb_ctx_t **out) {
       rc = PKB_ERR_CUDA;
       break;
     }
+    if (cudaHostAlloc(reinterpret_cast<void **>(&c->err_host), sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->err_dev), c->err_host, 0) != cudaSuccess) {
+      pkb::set_error("pkb_create: mapped error word: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = PKB_ERR_CUDA;
+      break;
+    }
+    *c->err_host = 0;
     rc = pkb::build_fbank_tables(c);
   } while (0);
   if (rc != PKB_OK) {
@@ -219,6 +236,7 @@ void pkb_destroy(pkb_ctx_t *c) {
   c->s_raw.release();
   c->s_out.release();
   c->s_flush.release();
+  if (c->err_host) cudaFreeHost(c->err_host);
   if (c->t0) cudaEventDestroy(c->t0);
   if (c->t1) cudaEventDestroy(c->t1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -227,8 +245,9 @@ void pkb_destroy(pkb_ctx_t *c) {
 
 int pkb_sync(pkb_ctx_t *c) {
   PKB_REQUIRE(c, "pkb_sync: ctx is NULL");
+  PKB_CUDA(cudaSetDevice(c->device));
   PKB_CUDA(cudaStreamSynchronize(c->stream));
-  return PKB_OK;
+  return pkb::check_device_error(c, "pkb_sync");
 }
 
 int pkb_device_sm_count(pkb_ctx_t *c) { return c ? c->sm_count : 0; }
@@ -255,7 +274,7 @@ int pkb_timer_stop(pkb_ctx_t *c, float *elapsed_ms) {
   PKB_CUDA(cudaEventRecord(c->t1, c->stream));
   PKB_CUDA(cudaEventSynchronize(c->t1));
   PKB_CUDA(cudaEventElapsedTime(elapsed_ms, c->t0, c->t1));
-  return PKB_OK;
+  return pkb::check_device_error(c, "pkb_timer_stop");
 }
 
 int pkb_profile_enable(pkb_ctx_t *c, int on) {

@@ -376,6 +376,7 @@ int build_fbank_tables(Ctx *c) {
     set_error("mel table has %zu entries (> 512)", ent.size());
     return PKB_ERR_INVALID;
   }
+  const size_t n_real = ent.size();
   while (ent.size() < 512) ent.push_back({kMel - 1, 0, 0.0f});
   std::vector<float4> melw(128);
   std::vector<uint32_t> melb(128), melc(32), mels(kMel, 0);
@@ -390,7 +391,11 @@ int build_fbank_tables(Ctx *c) {
       w[i & 3] = e.w;
       if ((i & 3) == 0) melb[(i >> 2) * 32 + l] = 0;
       melb[(i >> 2) * 32 + l] |= static_cast<uint32_t>(e.bin) << (8 * (i & 3));
-      bool flush = (i == 15) || ent[16 * l + i + 1].filter != e.filter;
+      // padding entries (weight 0 on bin 0, past the last real entry) never flush: they add an
+      // exact 0 to an accumulator nobody reads, instead of a fourth partial slot to filter 39
+      const size_t idx = static_cast<size_t>(16 * l + i);
+      const bool pad = idx >= n_real;
+      bool flush = !pad && ((i == 15) || idx + 1 == n_real || ent[idx + 1].filter != e.filter);
       if (flush) {
         mask |= 1u << i;
         if (first[e.filter] < 0) first[e.filter] = slot;
@@ -405,6 +410,11 @@ int build_fbank_tables(Ctx *c) {
     return PKB_ERR_INVALID;
   }
   for (int m = 0; m < kMel; ++m) {
+    // the kernel's combine step sums at most three partial slots per filter
+    if (count[m] < 1 || count[m] > 3) {
+      set_error("mel filter %d spans %d partial slots (kernel combines 1..3)", m, count[m]);
+      return PKB_ERR_INVALID;
+    }
     // slots of one filter are consecutive because entries are sorted by filter
     mels[m] = static_cast<uint32_t>(first[m]) | (static_cast<uint32_t>(count[m]) << 16);
   }

@@ -731,7 +731,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             red_release_add(p.tile_done + m_blk, 1);
             const long long t0 = clock64();
             while (ld_relaxed(p.tile_done + m_blk) < p.n_tiles_n) {
-              if (clock64() - t0 > 4000000000ll) __trap();
+              // A peer that never arrives (it cannot with a co-resident grid) must not hang the
+              // device, and a trap would poison the whole context: give up after ~20 s of
+              // cycles, leave an error code for the host (check_device_error) and carry on.
+              if (clock64() - t0 > 40000000000ll) {
+                if (p.err_flag != nullptr) *reinterpret_cast<volatile int *>(p.err_flag) = 1;
+                break;
+              }
             }
             (void)ld_acquire(p.tile_done + m_blk);
           }
@@ -888,9 +894,15 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
       set_error("launch_gemm: %d column tiles exceed the %d SMs of the device", p.n_tiles_n, c->sm_count);
       return PKB_ERR_UNSUPPORTED;
     }
+    if (max_units / p.n_tiles_n < 1) {
+      set_error("launch_gemm: %d column tiles of CTA %s do not fit the %d SMs of the device", p.n_tiles_n,
+                CG == 2 ? "pairs" : "singles", c->sm_count);
+      return PKB_ERR_UNSUPPORTED;
+    }
     pp.group_sched = 1;
     grid = CG * std::min(max_units / p.n_tiles_n, m_units) * p.n_tiles_n;
   }
+  pp.err_flag = c->err_dev;
   static const bool dbg_env = kProbes && getenv("PKB_GEMM_DEBUG") != nullptr;
   long long *dbg = nullptr;
   if (dbg_env) {

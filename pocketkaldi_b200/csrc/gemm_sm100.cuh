@@ -55,6 +55,7 @@ struct GemmParams {
   int *tile_done;      // final softmax: [m_tiles] arrival counters (zeroed by the launcher)
   const float *log_prior;  // [N_pad]
   float scale, log_floor;
+  int *err_flag;       // set by the launcher: mapped host word for "gave up waiting" reports
   long long *dbg;      // optional phase-cycle counters [grid][8] (PKB_GEMM_DEBUG=1), else nullptr
 };
 

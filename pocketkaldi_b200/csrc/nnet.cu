@@ -86,12 +86,6 @@ __global__ void pack_plain_kernel(const float *__restrict__ in, int64_t rows, in
   if (lo) lo[g] = operand_bits(v - operand_value(h, fp16), fp16);
 }
 
-__global__ void scale_kernel(float *x, int64_t n, float s) {
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    x[i] *= s;
-}
-
 // ---------------------------------------------------------------- weight packing
 // W[out][in] float -> BF16 planes [n_pad][k_pad]; column c of the source goes to
 // column remap(c) (identity, or the padded splice layout).
@@ -320,6 +314,13 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
   PKB_REQUIRE(in.rows == rows, "nnet_forward: input rows %lld != workspace rows %lld",
               static_cast<long long>(in.rows), static_cast<long long>(rows));
   const size_t ns = am->stages.size();
+  // AcousticModel::Compute (src/am.cc:106-112) floors and takes the log of the nnet output, which
+  // only means something for a SoftmaxLayer output; raw logits would silently differ from it
+  if (mode == kFinalLoglik && !am->softmax_last) {
+    set_error("log-likelihoods need a model whose last layer is a softmax (AcousticModel::Compute "
+              "takes log(max(p, 1e-20)) of the nnet output)");
+    return PKB_ERR_UNSUPPORTED;
+  }
   const __nv_bfloat16 *a_hi = in.hi, *a_lo = in.lo;
   int a_cols = in.cols, a_pitch = in.pitch_elems;
   const float *in_sumsq = nullptr;
@@ -373,7 +374,9 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
     static const bool no_pairs = getenv("PKB_GEMM_CG1") != nullptr;
     static const bool final_pairs = getenv("PKB_GEMM_FINAL_CG2") != nullptr;
     const bool want_pair = !final || am->planes == 2 || final_pairs;
-    const int cg = (want_pair && st.block_n == 256 && m_tiles >= 2 && !no_pairs) ? 2 : 1;
+    int cg = (want_pair && st.block_n == 256 && m_tiles >= 2 && !no_pairs) ? 2 : 1;
+    // the grouped schedule of the softmax stage needs one CTA (pair) per column tile on the device
+    if (final && p.final_mode != 0 && cg == 2 && (c->sm_count / 2) / p.n_tiles_n < 1) cg = 1;
     PKB_TRY(launch_gemm(c, st.block_n, am->planes, final, cg, &tm_a_hi, &tm_a_lo,
                         cg == 2 ? &st.tm_w_hi_half : &st.tm_w_hi,
                         cg == 2 ? &st.tm_w_lo_half : &st.tm_w_lo, p));
@@ -385,12 +388,6 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       in_sumsq = p.out_sumsq;
       in_sumsq_tiles = p.n_tiles_n * sumsq_parts(am->planes);
       in_dim = static_cast<float>(st.out_dim);
-    } else if (p.final_mode == 0 && prob_scale != 1.0f && mode == kFinalLoglik) {
-      const int64_t n = rows * st.out_dim;
-      const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(c->sm_count) * 8));
-      LaunchScope scope(c, PKB_KERNEL_MISC);
-      scale_kernel<<<grid, 256, 0, c->stream>>>(d_out, n, prob_scale);
-      PKB_CUDA(cudaGetLastError());
     }
   }
   return PKB_OK;

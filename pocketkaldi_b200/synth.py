@@ -5,7 +5,7 @@ any shard of a corpus can be regenerated on any host or GPU rank bit-for-bit
 (SURVEY.md section 8d). Only integer arithmetic is used: four 16-bit uniforms
 from a splitmix64 hash are summed (Irwin-Hall, n = 4) and scaled to sigma ~ 3000,
 which keeps |sample| <= 10392 (no clipping) and is identical in numpy and in the
-CUDA generator in pocketkaldi_b200/csrc/synth.cu.
+CUDA generator (synth_pcm_kernel in pocketkaldi_b200/csrc/cmvn.cu).
 """
 
 import numpy as np

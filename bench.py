@@ -392,7 +392,7 @@ def run_gpu_arm(args, cfg):
     main, am, batch = measure_batch(env, cfg, args.precision, n_utts, args.steps, args.warmup, True)
 
     # ---- end to end through the host-buffer API: pinned PCM in, log-likelihoods out, per chunk
-    e2e = None if args.no_e2e else run_e2e(env, cfg, am, n_utts)
+    e2e = None if args.no_e2e else run_e2e(env, cfg, am, n_utts, batch)
 
     # ---- parity sample (rank 0) and CPU baseline (rank 0, N=1 only)
     cpu = parity = other_modes = None
@@ -481,11 +481,14 @@ def sub_config(env, key, precision, with_parity, n_utts=None):
     return res
 
 
-def run_e2e(env, cfg, am, n_utts):
+def run_e2e(env, cfg, am, n_utts, main_batch=None):
     """PCM in pinned host memory -> H2D -> hot path -> D2H of the result into pinned host
     memory, chunk by chunk through the batch API, all inside the timed region. Two contexts
     (two CUDA streams, each with its own model copy and chunk batch) alternate so that the
-    D2H copy of chunk i overlaps the H2D + kernels of chunk i+1."""
+    D2H copy of chunk i overlaps the H2D + kernels of chunk i+1. With a model the result leaves
+    the GPU in the compact form (pkb_batch_set_compact: half bits + one FP32 offset per frame,
+    finished per look-up by pk_decodable_loglikelihood / pkb_loglik16_expand); --e2e-fp32 moves
+    the FP32 matrix instead."""
     import pocketkaldi_b200 as pk
     from pocketkaldi_b200.binding import PinnedArray
     from pocketkaldi_b200.synth import synth_pcm
@@ -493,7 +496,7 @@ def run_e2e(env, cfg, am, n_utts):
     chunk = min(args.e2e_chunk, n_utts)
     n_chunks = max(n_utts // chunk, 1)  # whole chunks only; the metric is a rate
     stages = (pk.STAGE_ALL | pk.STAGE_NO_FEATS) if cfg["nnet"] else (pk.STAGE_FBANK | pk.STAGE_CMVN)
-    which = pk.BUF_LOGLIK if cfg["nnet"] else pk.BUF_FEATS
+    compact = cfg["nnet"] and not args.e2e_fp32
     out_cols = cfg["pdfs"] if cfg["nnet"] else 40
     lanes = []
     for i in range(2):
@@ -503,21 +506,29 @@ def run_e2e(env, cfg, am, n_utts):
             a = pk.AcousticModel(c, precision_id(args.precision)).from_layers(
                 make_layers(cfg), uniform_prior(cfg), 5, 5)
         cb = pk.Batch(c, [SAMPLES_10S] * chunk, env.g, a, prob_scale=0.1)
+        if compact:
+            cb.set_compact(True)
         pin_in = PinnedArray((chunk * SAMPLES_10S,), np.int16)
-        pin_out = PinnedArray((cb.total_frames, out_cols), np.float32)
+        pin_out = PinnedArray((cb.total_frames, out_cols), np.uint16 if compact else np.float32)
+        pin_off = PinnedArray((cb.total_frames,), np.float32) if compact else None
         pin_in.array[:] = synth_pcm(1234, np.arange(chunk) + rank * n_utts + i * chunk,
                                     SAMPLES_10S).reshape(-1)
-        lanes.append((c, a, cb, pin_in, pin_out))
+        lanes.append((c, a, cb, pin_in, pin_out, pin_off))
     h2d = lanes[0][3].array.nbytes * n_chunks
-    d2h = lanes[0][4].array.nbytes * n_chunks
+    d2h = (lanes[0][4].array.nbytes + (lanes[0][5].array.nbytes if compact else 0)) * n_chunks
 
     def step():
         for k in range(n_chunks):
-            c, a, cb, pin_in, pin_out = lanes[k & 1]
+            c, a, cb, pin_in, pin_out, pin_off = lanes[k & 1]
             c.sync()  # this lane's previous chunk has fully landed in its pinned buffer
             cb.set_pcm(pin_in.array)
             cb.run(stages)
-            cb.get_rows_async(which, 0, cb.total_frames, pin_out.array)
+            if compact:
+                cb.get_rows_async(pk.BUF_LOGLIK16, 0, cb.total_frames, pin_out.array)
+                cb.get_rows_async(pk.BUF_LOGLIK_OFF, 0, cb.total_frames, pin_off.array)
+            else:
+                cb.get_rows_async(pk.BUF_LOGLIK if cfg["nnet"] else pk.BUF_FEATS, 0, cb.total_frames,
+                                  pin_out.array)
         for lane in lanes:
             lane[0].sync()
 
@@ -534,11 +545,27 @@ def run_e2e(env, cfg, am, n_utts):
     ms = max(ms, wall_ms)  # two streams: the host wall clock covers both lanes
     barrier(dist, local)
     ms_max, frames = reduce_timing(dist, local, ms, lanes[0][2].total_frames * n_chunks)
-    fin = bool(np.isfinite(lanes[0][4].array[::997]).all() and np.isfinite(lanes[1][4].array[::997]).all())
-    for i, (c, a, cb, pin_in, pin_out) in enumerate(lanes):
+    check = None
+    if compact:
+        fin = bool(np.isfinite(lanes[0][5].array).all() and np.isfinite(lanes[1][5].array).all())
+        if main_batch is not None:
+            # lane 0 holds the first utterances of the main batch: the expanded compact rows must
+            # agree with the FP32 rows of the device-resident run (unscaled bar: 2e-2)
+            n = FRAMES_10S
+            want = np.empty((n, out_cols), np.float32)
+            main_batch.get_rows_async(pk.BUF_LOGLIK, 0, n, want)
+            ctx.sync()
+            got = lanes[0][2].expand_compact(lanes[0][4].array[:n], lanes[0][5].array[:n], 0.1)
+            check = {"frames": n, "max_abs_err_unscaled_vs_fp32_output": float(np.max(np.abs(got - want)) / 0.1),
+                     "argmax_agreement_vs_fp32_output": float(np.mean(got.argmax(1) == want.argmax(1)))}
+    else:
+        fin = bool(np.isfinite(lanes[0][4].array[::997]).all() and np.isfinite(lanes[1][4].array[::997]).all())
+    for i, (c, a, cb, pin_in, pin_out, pin_off) in enumerate(lanes):
         cb.close()
         pin_in.free()
         pin_out.free()
+        if pin_off is not None:
+            pin_off.free()
         if i == 1:
             if cfg["nnet"]:
                 a.close()
@@ -547,6 +574,10 @@ def run_e2e(env, cfg, am, n_utts):
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
             "ms_per_step": ms_max / steps, "chunk_utts": chunk, "chunks_per_step": n_chunks,
             "d2h_gbs_per_gpu": d2h * steps / (ms_max * 1e-3) / 1e9,
+            "result_form": ("compact: fp16(loglik/prob_scale - off[frame]) + FP32 off[frame], %d B/frame; the "
+                            "consumer finishes prob_scale*(half+off) per look-up" % (2 * out_cols + 4))
+                           if compact else "FP32 matrix, %d B/frame" % (4 * out_cols),
+            "compact_check": check,
             "finite": fin, "timing": "host wall clock over both streams (>= the CUDA-event time of stream 0)",
             "api": "2 x (pkb_batch_set_pcm_i16 + pkb_batch_run + pkb_batch_get_rows), pinned host "
                    "buffers, two contexts alternating so D2H overlaps the next chunk"}
@@ -715,6 +746,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--e2e-fp32", action="store_true", help="e2e leg moves the FP32 matrix instead of the compact rows")
     ap.add_argument("--no-sub", action="store_true", help="skip the config 2/4/5 sub-objects")
     ap.add_argument("--no-modes", action="store_true", help="skip the other precision modes")
     ap.add_argument("--sub-utts4", type=int, default=512, help="utterances per GPU of the config-4 sub-run")

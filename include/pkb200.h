@@ -182,6 +182,10 @@ int pkb_pcm_to_loglik_i16(pkb_ctx_t *ctx, pkb_am_t *am, const int16_t *pcm,
 #define PKB_BUF_RAW 1    /* float  [frames][40] raw fbank   */
 #define PKB_BUF_FEATS 2  /* float  [frames][40] after CMVN  */
 #define PKB_BUF_LOGLIK 3 /* float  [frames][num_pdfs]       */
+/* compact output (pkb_batch_set_compact): IEEE half bits and one float offset per frame;
+ * loglik[t][p] = prob_scale * (half(LOGLIK16[t][p]) + LOGLIK_OFF[t])                  */
+#define PKB_BUF_LOGLIK16 4   /* uint16 [frames][num_pdfs] */
+#define PKB_BUF_LOGLIK_OFF 5 /* float  [frames]           */
 
 int pkb_batch_create(pkb_ctx_t *ctx, pkb_am_t *am, int n_utts, const int32_t *num_samples,
                      const float *global_stats, float prob_scale, pkb_batch_t **batch);
@@ -200,6 +204,21 @@ int pkb_batch_run(pkb_batch_t *batch, int stages);
 int pkb_batch_get(pkb_batch_t *batch, int which, void *host_dst);
 int pkb_batch_get_rows(pkb_batch_t *batch, int which, int64_t frame0, int64_t n_frames,
                        void *host_dst);
+/* SURVEY 8(f)-1, second half: the [frames x pdfs] FP32 matrix (12 KB per frame at 3000 pdfs) is
+ * what limits end-to-end throughput over PCIe. With the compact output on, the nnet stage writes
+ *   h[t][p]  = fp16( log(max(softmax(z)[p], 1e-20)) - log_prior[p] - off[t] )
+ *   off[t]   = max_p(z[p] - log_prior[p]) - logsumexp(z)        (FP32)
+ * instead of PKB_BUF_LOGLIK: half the bytes. The frame's best pdf is stored as exactly 0 and a
+ * value d below it carries at most d * 2^-11 of rounding error (<= 7.8e-3 up to d = 32), so the
+ * per-frame ordering of pdfs -- what the decoder compares -- is preserved. The consumer finishes
+ * prob_scale * (float(h) + off) per look-up (pk_decodable_loglikelihood, src/decodable.cc:24-31;
+ * pkb_loglik16_expand for a whole block). Needs a model that ends in a softmax.
+ * Switching releases the buffer of the other form. */
+int pkb_batch_set_compact(pkb_batch_t *batch, int on);
+/* Host-side expansion of a block of compact rows: out[t][p] = prob_scale * (half(h[t][p]) + off[t]).
+ * Does not touch the GPU. */
+int pkb_loglik16_expand(const uint16_t *h, const float *off, int64_t n_frames, int num_pdfs,
+                        float prob_scale, float *out);
 /* Sum over all elements of a per-frame float buffer, computed on the device
  * in double (a cheap whole-output fingerprint for full-size runs). */
 int pkb_batch_checksum(pkb_batch_t *batch, int which, double *sum_out);

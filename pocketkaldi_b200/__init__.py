@@ -37,5 +37,7 @@ from .binding import (  # noqa: F401
     BUF_RAW,
     BUF_FEATS,
     BUF_LOGLIK,
+    BUF_LOGLIK16,
+    BUF_LOGLIK_OFF,
     KERNEL_CLASSES,
 )

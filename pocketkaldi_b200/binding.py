@@ -23,6 +23,7 @@ PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2
 STAGE_FBANK, STAGE_CMVN, STAGE_NNET, STAGE_ALL = 1, 2, 4, 7
 STAGE_NO_FEATS = 8  # with STAGE_CMVN + a model: skip the FP32 copy of the CMVN features
 BUF_PCM, BUF_RAW, BUF_FEATS, BUF_LOGLIK = 0, 1, 2, 3
+BUF_LOGLIK16, BUF_LOGLIK_OFF = 4, 5  # compact output (Batch.set_compact)
 KERNEL_CLASSES = ("fbank", "cmvn", "gemm", "gemm_final", "misc")
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
@@ -91,6 +92,8 @@ _SIGNATURES = [
     ("pkb_batch_get", C.c_int, [_VP, C.c_int, _VP]),
     ("pkb_batch_get_rows", C.c_int, [_VP, C.c_int, C.c_int64, C.c_int64, _VP]),
     ("pkb_batch_checksum", C.c_int, [_VP, C.c_int, C.POINTER(C.c_double)]),
+    ("pkb_batch_set_compact", C.c_int, [_VP, C.c_int]),
+    ("pkb_loglik16_expand", C.c_int, [_VP, _VP, C.c_int64, C.c_int, C.c_float, _VP]),
     ("pkb_stream_create", C.c_int, [_VP, _VP, C.c_int, C.c_int, _f32p, C.c_float, C.POINTER(_VP)]),
     ("pkb_stream_destroy", None, [_VP]),
     ("pkb_stream_max_frames", C.c_int, [_VP]),
@@ -621,7 +624,24 @@ class Batch:
             return (self.total_samples,), np.int16
         if which in (BUF_RAW, BUF_FEATS):
             return (self.total_frames, 40), np.float32
+        if which == BUF_LOGLIK16:
+            return (self.total_frames, self.am.num_pdfs()), np.uint16
+        if which == BUF_LOGLIK_OFF:
+            return (self.total_frames,), np.float32
         return (self.total_frames, self.am.num_pdfs()), np.float32
+
+    def set_compact(self, on=True):
+        """Half-size output of the nnet stage (see pkb_batch_set_compact in include/pkb200.h)."""
+        _check(self.ctx.lib.pkb_batch_set_compact(self.h, 1 if on else 0))
+
+    def expand_compact(self, h16, off, prob_scale):
+        """prob_scale * (half(h16) + off[:, None]) through the library's host helper."""
+        h16 = np.ascontiguousarray(h16, dtype=np.uint16)
+        off = np.ascontiguousarray(off, dtype=np.float32)
+        out = np.empty(h16.shape, np.float32)
+        _check(self.ctx.lib.pkb_loglik16_expand(h16.ctypes.data, off.ctypes.data, h16.shape[0],
+                                                h16.shape[1], prob_scale, out.ctypes.data))
+        return out
 
     def get(self, which, out=None):
         shape, dt = self._shape(which)

@@ -277,6 +277,8 @@ struct pkb_batch {
   float prob_scale = 1.0f;
   float global_stats[PKB_CMVN_STATS_DIM];
   pkb::DevBuf pcm, raw, feats, loglik, sum;
+  bool compact = false;             // nnet stage writes loglik16 + loglik_off instead of loglik
+  pkb::DevBuf loglik16, loglik_off;
   Workspace ws;
   pkb::PaddedPlanes planes;
   int64_t padded = 0, gemm_rows = 0;
@@ -422,7 +424,7 @@ int pkb_am_compute(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t
   const BatchMeta &m = am->meta;
   if (m.total_frames == 0) return PKB_OK;
   PKB_REQUIRE(loglik_out != nullptr, "pkb_am_compute: loglik_out is NULL");
-  PKB_TRY(pkb::copy_rows_compact(c, loglik_out, am->out_f32.as<float>(), m, pad_off, am->num_pdfs, 0,
+  PKB_TRY(pkb::copy_rows_compact(c, loglik_out, am->out_f32.p, m, pad_off, am->num_pdfs, 0,
                                  m.total_frames));
   PKB_CUDA(cudaStreamSynchronize(c->stream));
   return pkb::check_device_error(c, "pkb_am_compute");
@@ -501,7 +503,7 @@ int pkb_am_compute_chunked(pkb_ctx_t *c, pkb_am_t *am, const float *feats, int32
   for (int i = 0; i < n_chunks; ++i) {
     const int64_t r0 = static_cast<int64_t>(i) * chunk_frames;
     const int64_t n = std::min<int64_t>(chunk_frames, num_frames - r0);
-    PKB_TRY(pkb::copy_rows_compact(c, loglik_out + r0 * am->num_pdfs, am->out_f32.as<float>(), m,
+    PKB_TRY(pkb::copy_rows_compact(c, loglik_out + r0 * am->num_pdfs, am->out_f32.p, m,
                                    pad_off, am->num_pdfs, r0, n));
     PKB_TRY(pkb_event_record(c, events[i]));
   }
@@ -630,6 +632,8 @@ void pkb_batch_destroy(pkb_batch_t *b) {
   b->raw.release();
   b->feats.release();
   b->loglik.release();
+  b->loglik16.release();
+  b->loglik_off.release();
   b->sum.release();
   b->ws.release();
   b->meta.dev.release();
@@ -676,8 +680,51 @@ int pkb_batch_run(pkb_batch_t *b, int stages) {
     in.rows = b->gemm_rows;
     in.cols = (am->left + am->right + 1) * am->feat_dim_pad;
     in.pitch_elems = am->feat_dim_pad;
-    PKB_TRY(pkb::nnet_forward(am, &b->ws, in, &am->splice_stage, pkb::kFinalLoglik, b->prob_scale,
-                              b->loglik.as<float>()));
+    if (b->compact)
+      PKB_TRY(pkb::nnet_forward(am, &b->ws, in, &am->splice_stage, pkb::kFinalCompact, b->prob_scale,
+                                nullptr, b->loglik16.as<uint16_t>(), b->loglik_off.as<float>()));
+    else
+      PKB_TRY(pkb::nnet_forward(am, &b->ws, in, &am->splice_stage, pkb::kFinalLoglik, b->prob_scale,
+                                b->loglik.as<float>()));
+  }
+  return PKB_OK;
+}
+
+int pkb_batch_set_compact(pkb_batch_t *b, int on) {
+  PKB_REQUIRE(b, "pkb_batch_set_compact: batch is NULL");
+  PKB_REQUIRE(b->am, "pkb_batch_set_compact: the batch has no model");
+  if ((on != 0) == b->compact) return PKB_OK;
+  PKB_REQUIRE(!on || b->am->softmax_last, "pkb_batch_set_compact: the model does not end in a softmax");
+  PKB_CUDA(cudaSetDevice(b->c->device));
+  PKB_CUDA(cudaStreamSynchronize(b->c->stream));  // nothing may still be writing the buffer we free
+  const size_t elems = std::max<size_t>(4, static_cast<size_t>(b->gemm_rows) * b->am->num_pdfs);
+  if (on) {
+    b->loglik.release();
+    PKB_TRY(b->loglik16.ensure(elems * sizeof(uint16_t)));
+    PKB_TRY(b->loglik_off.ensure(std::max<size_t>(4, static_cast<size_t>(b->gemm_rows) * sizeof(float))));
+  } else {
+    b->loglik16.release();
+    b->loglik_off.release();
+    PKB_TRY(b->loglik.ensure(elems * sizeof(float)));
+  }
+  b->compact = on != 0;
+  return PKB_OK;
+}
+
+int pkb_loglik16_expand(const uint16_t *h, const float *off, int64_t n_frames, int num_pdfs,
+                        float prob_scale, float *out) {
+  PKB_REQUIRE(n_frames >= 0 && num_pdfs >= 0, "pkb_loglik16_expand: negative size");
+  if (n_frames == 0 || num_pdfs == 0) return PKB_OK;
+  PKB_REQUIRE(h && off && out, "pkb_loglik16_expand: NULL argument");
+  for (int64_t t = 0; t < n_frames; ++t) {
+    const uint16_t *row = h + t * num_pdfs;
+    float *dst = out + t * num_pdfs;
+    const float o = off[t];
+    for (int p = 0; p < num_pdfs; ++p) {
+      __half_raw r;
+      r.x = row[p];
+      dst[p] = prob_scale * (__half2float(__half(r)) + o);
+    }
   }
   return PKB_OK;
 }
@@ -701,8 +748,17 @@ static int batch_buf(pkb_batch_t *b, int which, char **ptr, size_t *row_bytes, i
       return PKB_OK;
     case PKB_BUF_LOGLIK:
       PKB_REQUIRE(b->am, "batch has no model: no log-likelihood buffer");
+      PKB_REQUIRE(!b->compact, "the batch writes the compact output: read PKB_BUF_LOGLIK16 / PKB_BUF_LOGLIK_OFF");
       *ptr = b->loglik.as<char>();
       *row_bytes = static_cast<size_t>(b->am->num_pdfs) * sizeof(float);
+      *rows = b->meta.total_frames;
+      return PKB_OK;
+    case PKB_BUF_LOGLIK16:
+    case PKB_BUF_LOGLIK_OFF:
+      PKB_REQUIRE(b->am && b->compact, "the compact output is off (pkb_batch_set_compact)");
+      *ptr = which == PKB_BUF_LOGLIK16 ? b->loglik16.as<char>() : b->loglik_off.as<char>();
+      *row_bytes = which == PKB_BUF_LOGLIK16 ? static_cast<size_t>(b->am->num_pdfs) * sizeof(uint16_t)
+                                             : sizeof(float);
       *rows = b->meta.total_frames;
       return PKB_OK;
   }
@@ -722,9 +778,15 @@ int pkb_batch_get_rows(pkb_batch_t *b, int which, int64_t row0, int64_t n_rows, 
   if (n_rows == 0) return PKB_OK;
   PKB_REQUIRE(host_dst, "pkb_batch_get_rows: host_dst is NULL");
   PKB_CUDA(cudaSetDevice(b->c->device));
-  if (which == PKB_BUF_LOGLIK)  // stored with padded rows: compact per utterance on the way out
-    return pkb::copy_rows_compact(b->c, host_dst, b->loglik.as<float>(), b->meta, b->pad_off,
-                                  b->am->num_pdfs, row0, n_rows);
+  // stored with padded rows: compacted per utterance on the way out
+  if (which == PKB_BUF_LOGLIK)
+    return pkb::copy_rows_compact(b->c, host_dst, b->loglik.p, b->meta, b->pad_off, b->am->num_pdfs, row0,
+                                  n_rows);
+  if (which == PKB_BUF_LOGLIK16)
+    return pkb::copy_rows_compact(b->c, host_dst, b->loglik16.p, b->meta, b->pad_off, b->am->num_pdfs,
+                                  row0, n_rows, sizeof(uint16_t));
+  if (which == PKB_BUF_LOGLIK_OFF)
+    return pkb::copy_rows_compact(b->c, host_dst, b->loglik_off.p, b->meta, b->pad_off, 1, row0, n_rows);
   PKB_CUDA(cudaMemcpyAsync(host_dst, ptr + row0 * row_bytes, n_rows * row_bytes,
                            cudaMemcpyDeviceToHost, b->c->stream));
   return PKB_OK;
@@ -741,7 +803,8 @@ int pkb_batch_get(pkb_batch_t *b, int which, void *host_dst) {
 
 int pkb_batch_checksum(pkb_batch_t *b, int which, double *sum_out) {
   PKB_REQUIRE(b && sum_out, "pkb_batch_checksum: NULL argument");
-  PKB_REQUIRE(which != PKB_BUF_PCM, "pkb_batch_checksum: float buffers only");
+  PKB_REQUIRE(which != PKB_BUF_PCM && which != PKB_BUF_LOGLIK16 && which != PKB_BUF_LOGLIK_OFF,
+              "pkb_batch_checksum: FP32 per-frame buffers only");
   PKB_CUDA(cudaSetDevice(b->c->device));
   char *ptr = nullptr;
   size_t row_bytes = 0;

@@ -355,7 +355,8 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool 
   L.stage_bytes = planes * (L.a_plane + L.w_plane);
   // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
   // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch per team
-  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 3 * 128 * 8 : epi_warps(false, planes) * planes * 4096;
+  // (and per row one more float for the compact mode's max(z - log_prior))
+  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 3 * 128 * 8 + 3 * 128 * 4 : epi_warps(false, planes) * planes * 4096;
   uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */ - L.epi_bytes;
   L.stages = avail / L.stage_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
@@ -664,11 +665,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         // ---- pass 1 (softmax only): per-row (max, sum exp) over this warp's half of the
         //      tile's columns, exchanged with the warps / CTAs that own the other columns
         constexpr int kChunks = BN / 32 / kHalves;  // 32-column chunks per epilogue warp
+#if PKB_FINAL_TEAMS == 2
+        static_assert(kChunks % 2 == 0, "the compact output packs two 32-column chunks per staging row");
+#endif
         const int cbase = chalf * (BN / kHalves);
         const float kLog2e = 1.4426950408889634f;
-        float lse = 0.0f;
+        float lse = 0.0f, off16 = 0.0f;
         if (p.final_mode != 0) {
           float run_max = -INFINITY, run_sum = 0.0f;
+          float run_mzl = -INFINITY;  // compact mode: max over columns of z - log_prior
+          const bool compact = p.final_mode == 3;
 #pragma unroll 1
           for (int c = 0; c < kChunks; ++c) {
             const int col0 = n0 + cbase + c * 32;
@@ -694,6 +700,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             float cmax = z[0];
 #pragma unroll
             for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, z[i]);
+            if (compact) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 lp = *reinterpret_cast<const float4 *>(s_lp + cbase + c * 32 + i);
+                run_mzl = fmaxf(run_mzl, fmaxf(fmaxf(z[i] - lp.x, z[i + 1] - lp.y),
+                                               fmaxf(z[i + 2] - lp.z, z[i + 3] - lp.w)));
+              }
+            }
             const float nm = fmaxf(run_max, cmax);
             const float off = -nm * kLog2e;
             float acc = 0.0f;
@@ -708,7 +722,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           const int rit = q * 32 + lane;  // row inside the tile
           // (kTeams * (kHalves - 1) == 2 or 3 scratch planes of 128 rows)
           float2 *s_half = reinterpret_cast<float2 *>(s_lp + BN) + team * (kHalves - 1) * kBlockM;
-          if (chalf != 0) s_half[(chalf - 1) * kBlockM + rit] = make_float2(run_max, run_sum);
+          float *s_half_mzl = reinterpret_cast<float *>(reinterpret_cast<float2 *>(s_lp + BN) + 3 * kBlockM) +
+                              team * (kHalves - 1) * kBlockM;
+          if (chalf != 0) {
+            s_half[(chalf - 1) * kBlockM + rit] = make_float2(run_max, run_sum);
+            if (compact) s_half_mzl[(chalf - 1) * kBlockM + rit] = run_mzl;
+          }
           if (dbg_on) tk2 = clock64();
           named_bar_sync(1 + team, kTeamThreads);
           float2 *xbase = p.lse_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
@@ -722,6 +741,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               nm = m2;
             }
             __stcg(&xbase[n_blk * kBlockM + rit], make_float2(nm, sm));
+            if (compact) {
+              float mz = run_mzl;
+#pragma unroll
+              for (int h = 0; h < kHalves - 1; ++h) mz = fmaxf(mz, s_half_mzl[h * kBlockM + rit]);
+              __stcg(&p.mzl_part[(static_cast<size_t>(m_blk) * p.n_tiles_n + n_blk) * kBlockM + rit], mz);
+            }
           }
           named_bar_sync(1 + team, kTeamThreads);
           // (2) one thread releases the CTA's partials device-wide (the named barrier orders the
@@ -753,6 +778,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               mx = nm;
             }
             lse = mx + logf(ssum);
+            if (compact) {
+              const float *zbase = p.mzl_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
+              float mz = -INFINITY;
+              for (int j = 0; j < p.n_tiles_n; ++j) mz = fmaxf(mz, __ldcg(&zbase[j * kBlockM + rit]));
+              // reference point of this frame's 16-bit values: the largest max(z - lse, floor) - lp
+              // unless the floor binds (softmax below 1e-20), which only moves the point
+              off16 = mz - lse;
+              if (n_blk == 0 && chalf == 0 && row_ok) p.out_off[row] = off16;
+            }
           }
         }
         if (dbg_on) tk4 = clock64();
@@ -762,6 +796,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         //      fills that gap).
         const bool vec_ok = (p.ld_f32 & 3) == 0;
         const float floor_v = p.log_floor, sc = p.scale;
+        if (p.final_mode == 3) {
+          // compact: two 32-column chunks fill one 128-byte staging row of halves
+          const bool vec16_ok = (p.ld_f32 & 7) == 0;
+#pragma unroll 1
+          for (int c = 0; c < kChunks; c += 2) {
+            const int col0 = n0 + cbase + c * 32;
+            if (p.N_valid - col0 <= 0) break;
+            uint32_t hbits[32];
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+              uint32_t v[32];
+              tmem_ld32(taddr + cbase + (c + hc) * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b = *reinterpret_cast<const float4 *>(s_bias + cbase + (c + hc) * 32 + i);
+                const float4 lp = *reinterpret_cast<const float4 *>(s_lp + cbase + (c + hc) * 32 + i);
+                const float t0 = fmaxf(fmaf(__uint_as_float(v[i + 0]), rs, b.x) - lse, floor_v) - lp.x - off16;
+                const float t1 = fmaxf(fmaf(__uint_as_float(v[i + 1]), rs, b.y) - lse, floor_v) - lp.y - off16;
+                const float t2 = fmaxf(fmaf(__uint_as_float(v[i + 2]), rs, b.z) - lse, floor_v) - lp.z - off16;
+                const float t3 = fmaxf(fmaf(__uint_as_float(v[i + 3]), rs, b.w) - lse, floor_v) - lp.w - off16;
+                hbits[hc * 16 + i / 2] = pack_f16(t0, t1);
+                hbits[hc * 16 + i / 2 + 1] = pack_f16(t2, t3);
+              }
+            }
+            if (vec16_ok) {
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                st_shared_v4(stg_w + ((j ^ (lane & 7)) << 4), hbits[4 * j], hbits[4 * j + 1], hbits[4 * j + 2],
+                             hbits[4 * j + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tm_out, smem_u32(stg), col0, wrow0);
+                tma_store_commit();
+              }
+            } else if (row_ok) {
+              uint16_t *dst = p.out_h16 + static_cast<size_t>(row) * p.ld_f32 + col0;
+#pragma unroll
+              for (int i = 0; i < 64; ++i)
+                if (col0 + i < p.N_valid)
+                  dst[i] = static_cast<uint16_t>((i & 1) ? (hbits[i >> 1] >> 16) : (hbits[i >> 1] & 0xffffu));
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c) {
           const int col0 = n0 + cbase + c * 32;
@@ -827,6 +908,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               if (i < nvalid) dst[i] = z[i];
           }
         }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -878,8 +960,11 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
                const CUtensorMap *w_lo, const GemmParams &p) {
   // FP32 output map of the final stage (hidden stages pass a dummy copy of the A map)
   CUtensorMap out_map = *a_hi;
-  if (FINAL && (p.ld_f32 & 3) == 0)
+  if (FINAL && p.final_mode == 3) {
+    if ((p.ld_f32 & 7) == 0) PKB_TRY(make_output_map16(&out_map, p.out_h16, p.N_valid, p.M));
+  } else if (FINAL && (p.ld_f32 & 3) == 0) {
     PKB_TRY(make_output_map(&out_map, p.out_f32, p.N_valid, p.M));
+  }
   const SmemLayout L = smem_layout(BN, PLANES, FINAL, CG);
   auto kern = gemm_kernel<BN, PLANES, FINAL, CG>;
   PKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -936,7 +1021,13 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
       attr[1].id = cudaLaunchAttributeCooperative;
       attr[1].val.cooperative = 1;
       cfg.attrs = attr;
-      cfg.numAttrs = 2;
+      // Nsight Compute rejects a cooperative launch of a cluster kernel (LaunchFailed, grid shown
+      // as 0). Under an injected tool kernels are serialised anyway, so co-residency of the
+      // grid (<= one CTA per SM) holds without the attribute.
+      static const bool tool_attached = getenv("CUDA_INJECTION64_PATH") != nullptr ||
+                                        getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
+                                        getenv("PKB_NO_COOP_CLUSTER") != nullptr;
+      cfg.numAttrs = tool_attached ? 1 : 2;
       PKB_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, m2, m3, out_map, pp));
     }
   } else if (CG == 2) {
@@ -1018,6 +1109,27 @@ int make_output_map(CUtensorMap *map, const float *base, uint64_t cols, uint64_t
                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (output) failed (CUresult %d) cols=%llu rows=%llu", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows);
+    return PKB_ERR_CUDA;
+  }
+  return PKB_OK;
+}
+
+int make_output_map16(CUtensorMap *map, const uint16_t *base, uint64_t cols, uint64_t rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return PKB_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(uint16_t)};
+  cuuint32_t box[2] = {64, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t *>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (16-bit output) failed (CUresult %d) cols=%llu rows=%llu", (int)r,
               (unsigned long long)cols, (unsigned long long)rows);
     return PKB_ERR_CUDA;
   }

@@ -49,8 +49,15 @@ struct GemmParams {
   int ld_out;
   float *out_f32;      // final: [M][ld_f32], GEMM row m -> output row m (padded-row layout)
   int ld_f32;
-  // final_mode: 0 raw logits, 1 softmax probabilities, 2 scale*(max(log softmax, log_floor) - log_prior)
+  // final_mode: 0 raw logits, 1 softmax probabilities, 2 scale*(max(log softmax, log_floor) - log_prior),
+  // 3 compact log-likelihoods: t = max(log softmax, log_floor) - log_prior is written as
+  //   out_h16[row][col] = fp16(t - off[row]),  out_off[row] = max_col(z - log_prior) - lse
+  // i.e. half the bytes, exact at the top of every frame (the values a decoder compares), the
+  // consumer finishes prob_scale * (float(h) + off) (pk_decodable_loglikelihood, src/decodable.cc:24-31)
   int final_mode;
+  uint16_t *out_h16;   // compact: [M][ld_f32] IEEE half bits (padded-row layout like out_f32)
+  float *out_off;      // compact: [M]
+  float *mzl_part;     // compact: [M][n_tiles_n] per-tile max(z - log_prior), exchanged like lse_part
   float2 *lse_part;    // final softmax: [M][n_tiles_n] (max, sum exp) exchanged between column tiles
   int *tile_done;      // final softmax: [m_tiles] arrival counters (zeroed by the launcher)
   const float *log_prior;  // [N_pad]
@@ -75,6 +82,8 @@ int launch_gemm(Ctx *c, int block_n, int planes, bool final, int cta_group, cons
 // FP32 [rows][cols] output map for the final stage's TMA stores: box {32 cols, 32 rows},
 // 128-byte swizzle. Needs cols % 4 == 0 (16-byte row pitch).
 int make_output_map(CUtensorMap *map, const float *base, uint64_t cols, uint64_t rows);
+// Same for the compact 16-bit output: box {64 cols, 32 rows}. Needs cols % 8 == 0.
+int make_output_map16(CUtensorMap *map, const uint16_t *base, uint64_t cols, uint64_t rows);
 
 int gemm_max_smem_bytes(int block_n, int planes);
 

@@ -151,6 +151,7 @@ void Workspace::release() {
     sumsq[i].release();
   }
   lse_part.release();
+  mzl_part.release();
   tile_done.release();
   row_map.release();
   feat_hi.release();
@@ -300,12 +301,14 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
   const Stage &last = am->stages.back();
   PKB_TRY(ws->lse_part.ensure(static_cast<size_t>((rows + kBlockM - 1) / kBlockM) * kBlockM *
                               2 * (last.n_pad / last.block_n) * sizeof(float2)));
+  PKB_TRY(ws->mzl_part.ensure(static_cast<size_t>((rows + kBlockM - 1) / kBlockM) * kBlockM *
+                              2 * (last.n_pad / last.block_n) * sizeof(float)));
   PKB_TRY(ws->tile_done.ensure(sizeof(int) * (static_cast<size_t>((rows + kBlockM - 1) / kBlockM) + 1)));
   return PKB_OK;
 }
 
 int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *first,
-                 FinalMode mode, float prob_scale, float *d_out) {
+                 FinalMode mode, float prob_scale, float *d_out, uint16_t *d_h16, float *d_off) {
   Ctx *c = am->c;
   const int64_t rows = ws->rows;
   if (rows == 0) return PKB_OK;
@@ -316,7 +319,7 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
   const size_t ns = am->stages.size();
   // AcousticModel::Compute (src/am.cc:106-112) floors and takes the log of the nnet output, which
   // only means something for a SoftmaxLayer output; raw logits would silently differ from it
-  if (mode == kFinalLoglik && !am->softmax_last) {
+  if ((mode == kFinalLoglik || mode == kFinalCompact) && !am->softmax_last) {
     set_error("log-likelihoods need a model whose last layer is a softmax (AcousticModel::Compute "
               "takes log(max(p, 1e-20)) of the nnet output)");
     return PKB_ERR_UNSUPPORTED;
@@ -360,7 +363,13 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       p.out_f32 = d_out;
       p.ld_f32 = st.out_dim;
       // softmax + AM epilogue are fused into this GEMM (no second pass over the output)
-      p.final_mode = am->softmax_last ? (mode == kFinalLoglik ? 2 : (mode == kFinalProb ? 1 : 0)) : 0;
+      p.final_mode = am->softmax_last ? (mode == kFinalCompact ? 3 : (mode == kFinalLoglik ? 2 : (mode == kFinalProb ? 1 : 0))) : 0;
+      if (p.final_mode == 3) {
+        PKB_REQUIRE(d_h16 && d_off, "nnet_forward: the compact output needs its two buffers");
+        p.out_h16 = d_h16;
+        p.out_off = d_off;
+        p.mzl_part = ws->mzl_part.as<float>();
+      }
       p.lse_part = ws->lse_part.as<float2>();
       p.tile_done = ws->tile_done.as<int>();
       p.log_prior = am->log_prior.as<float>();
@@ -393,8 +402,9 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
   return PKB_OK;
 }
 
-int copy_rows_compact(Ctx *c, void *host_dst, const float *d_padded, const BatchMeta &m,
-                      const std::vector<int64_t> &pad_off, int cols, int64_t frame0, int64_t n) {
+int copy_rows_compact(Ctx *c, void *host_dst, const void *d_padded, const BatchMeta &m,
+                      const std::vector<int64_t> &pad_off, int cols, int64_t frame0, int64_t n,
+                      size_t elem_bytes) {
   if (n <= 0) return PKB_OK;
   // first utterance whose frame range reaches past frame0
   int u = static_cast<int>(std::upper_bound(m.frame_off.begin(), m.frame_off.end(), frame0) -
@@ -402,7 +412,7 @@ int copy_rows_compact(Ctx *c, void *host_dst, const float *d_padded, const Batch
   if (u < 0) u = 0;
   const int64_t end = frame0 + n;
   char *dst = static_cast<char *>(host_dst);
-  const size_t row_bytes = static_cast<size_t>(cols) * sizeof(float);
+  const size_t row_bytes = static_cast<size_t>(cols) * elem_bytes;
   while (u < m.n_utts && m.frame_off[u] < end) {
     const int64_t a = std::max<int64_t>(frame0, m.frame_off[u]);
     const int64_t b = std::min<int64_t>(end, m.frame_off[u + 1]);

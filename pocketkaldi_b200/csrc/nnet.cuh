@@ -26,6 +26,7 @@ enum FinalMode {
   kFinalRaw = 0,     // z                                   (stack without SoftmaxLayer)
   kFinalProb = 1,    // softmax(z)                          (Nnet::Propagate, src/nnet.cc:149-163)
   kFinalLoglik = 2,  // s*(log(max(softmax(z),1e-20))-lp)   (AcousticModel::Compute + decodable scale)
+  kFinalCompact = 3, // fp16(log(max(softmax(z),1e-20)) - lp - off[row]) + off[row]: half the bytes
 };
 
 // A [rows][cols] BF16 matrix (one or two planes) as the first GEMM's A operand.
@@ -40,7 +41,7 @@ struct InputView {
 // Per-batch scratch of the forward pass.
 struct Workspace {
   int64_t rows = 0;  // M of every GEMM
-  DevBuf act_hi[2], act_lo[2], sumsq[2], lse_part, tile_done, row_map;
+  DevBuf act_hi[2], act_lo[2], sumsq[2], lse_part, mzl_part, tile_done, row_map;
   // padded feature planes of the batch pipeline
   DevBuf feat_hi, feat_lo, pad_off;
   void release();
@@ -87,13 +88,17 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows);
 // am->splice_stage). d_out is [ws->rows][out_dim]: GEMM row m -> output row m. For a padded
 // batch the rows of utterance u start at pad_off[u] and the (left+right) rows between two
 // utterances hold garbage; copy_rows_compact() removes them on the way out.
+// kFinalCompact writes d_h16 [ws->rows][out_dim] (IEEE half bits) and d_off [ws->rows] instead of
+// d_out; prob_scale is then left to the consumer.
 int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *first,
-                 FinalMode mode, float prob_scale, float *d_out);
+                 FinalMode mode, float prob_scale, float *d_out, uint16_t *d_h16 = nullptr,
+                 float *d_off = nullptr);
 
 // Device (padded rows) -> host (compact frames) copy of frames [frame0, frame0 + n): one
 // cudaMemcpyAsync per utterance touched.
-int copy_rows_compact(Ctx *c, void *host_dst, const float *d_padded, const BatchMeta &m,
-                      const std::vector<int64_t> &pad_off, int cols, int64_t frame0, int64_t n);
+int copy_rows_compact(Ctx *c, void *host_dst, const void *d_padded, const BatchMeta &m,
+                      const std::vector<int64_t> &pad_off, int cols, int64_t frame0, int64_t n,
+                      size_t elem_bytes = sizeof(float));
 
 // Sum over the valid rows (row_map[m] >= 0) of a padded [rows][cols] matrix, in double.
 int launch_checksum_rows(Ctx *c, const float *d, int cols, int64_t rows, const int32_t *row_map,

@@ -1,4 +1,4 @@
-// pocketkaldi_b200_batch <model-file> <list.scp | x.wav> [--threads N] [--batch-utts M]
+// pocketkaldi_b200_batch <model-file> <list.scp | x.wav> [--threads N] [--batch-utts M] [--compact 0|1]
 //
 // Batch counterpart of the reference CLI (src/main.cc): same arguments, same
 // "<file>\t<hyp>\t<loglikelihood per frame>" lines in list order, but
@@ -43,11 +43,13 @@ struct Result {
 };
 
 // The decode half of pk_process (src/pocketkaldi.cc:209-243) over an attached decodable.
-Result decode_one(pk_t *rec, float *rows, int frames, pkb_event_t *ready) {
+Result decode_one(pk_t *rec, float *rows, const uint16_t *rows16, const float *off, int frames,
+                  pkb_event_t *ready) {
   Result r;
   Decoder decoder(rec->fst);
   pk_decodable_t dec;
-  pk_decodable_attach(&dec, rec->am, rows, frames, ready);
+  if (rows16 != nullptr) pk_decodable_attach_compact(&dec, rec->am, rows16, off, frames, 0.1f, ready);
+  else pk_decodable_attach(&dec, rec->am, rows, frames, ready);
   decoder.Decode(&dec);
   Decoder::Hypothesis hyp = decoder.BestPath();
   std::vector<int> words = hyp.words();
@@ -73,9 +75,13 @@ int main(int argc, char **argv) {
   }
   int n_threads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
   int batch_utts = 256;
+  // compact rows (half the PCIe bytes, finished per look-up) are the default; --compact 0 moves
+  // the FP32 matrix like pk_decodable_init does
+  bool compact = true;
   for (int i = 3; i + 1 < argc; i += 2) {
     if (strcmp(argv[i], "--threads") == 0) n_threads = std::max(1, atoi(argv[i + 1]));
     else if (strcmp(argv[i], "--batch-utts") == 0) batch_utts = std::max(1, atoi(argv[i + 1]));
+    else if (strcmp(argv[i], "--compact") == 0) compact = atoi(argv[i + 1]) != 0;
   }
   const char *model_file = argv[1], *input_file = argv[2];
 
@@ -114,18 +120,26 @@ int main(int argc, char **argv) {
     const int64_t frames = frame_off[n];
     pkb_batch_t *batch = nullptr;
     CHECK(pkb_batch_create(ctx, am, n, num_samples + first, rec.cmvn_global_stats->data, 0.1f, &batch));
-    void *pcm = nullptr, *ll = nullptr;
+    void *pcm = nullptr, *ll = nullptr, *off = nullptr;
+    if (compact) CHECK(pkb_batch_set_compact(batch, 1));
     CHECK(pkb_host_alloc(&pcm, std::max<int64_t>(samples, 1) * sizeof(int16_t)));
-    CHECK(pkb_host_alloc(&ll, std::max<int64_t>(frames, 1) * pdfs * sizeof(float)));
+    CHECK(pkb_host_alloc(&ll, std::max<int64_t>(frames, 1) * pdfs * (compact ? sizeof(uint16_t) : sizeof(float))));
+    CHECK(pkb_host_alloc(&off, std::max<int64_t>(frames, 1) * sizeof(float)));
     CHECK(pkb_wavlist_read_i16(list, first, n, static_cast<int16_t *>(pcm), n_threads));
     CHECK(pkb_batch_set_pcm_i16(batch, static_cast<const int16_t *>(pcm)));
     CHECK(pkb_batch_run(batch, PKB_STAGE_ALL));
     std::vector<pkb_event_t *> ready(n, nullptr);
     for (int u = 0; u < n; ++u) {
       const int64_t T = frame_off[u + 1] - frame_off[u];
-      if (T > 0)
+      if (T > 0 && compact) {
+        CHECK(pkb_batch_get_rows(batch, PKB_BUF_LOGLIK16, frame_off[u], T,
+                                 static_cast<uint16_t *>(ll) + frame_off[u] * pdfs));
+        CHECK(pkb_batch_get_rows(batch, PKB_BUF_LOGLIK_OFF, frame_off[u], T,
+                                 static_cast<float *>(off) + frame_off[u]));
+      } else if (T > 0) {
         CHECK(pkb_batch_get_rows(batch, PKB_BUF_LOGLIK, frame_off[u], T,
                                  static_cast<float *>(ll) + frame_off[u] * pdfs));
+      }
       CHECK(pkb_event_create(ctx, &ready[u]));
       CHECK(pkb_event_record(ctx, ready[u]));
     }
@@ -135,8 +149,11 @@ int main(int argc, char **argv) {
         const int u = next.fetch_add(1);
         if (u >= n) return;
         if (num_samples[first + u] == 0) continue;  // pk_process: empty utterance -> empty hyp
-        results[first + u] = decode_one(&rec, static_cast<float *>(ll) + frame_off[u] * pdfs,
-                                        static_cast<int>(frame_off[u + 1] - frame_off[u]), ready[u]);
+        results[first + u] = decode_one(
+            &rec, compact ? nullptr : static_cast<float *>(ll) + frame_off[u] * pdfs,
+            compact ? static_cast<uint16_t *>(ll) + frame_off[u] * pdfs : nullptr,
+            static_cast<float *>(off) + frame_off[u], static_cast<int>(frame_off[u + 1] - frame_off[u]),
+            ready[u]);
       }
     };
     std::vector<std::thread> pool;
@@ -146,6 +163,7 @@ int main(int argc, char **argv) {
     for (pkb_event_t *e : ready) pkb_event_destroy(e);
     pkb_host_free(pcm);
     pkb_host_free(ll);
+    pkb_host_free(off);
     pkb_batch_destroy(batch);
   }
   for (int i = 0; i < n_files; ++i)

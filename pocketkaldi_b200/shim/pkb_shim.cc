@@ -212,7 +212,35 @@ struct pkb_lazy_decodable {
   int chunk = 0;
   pkb_event_t *attached = nullptr;  // attach mode: the caller's event (not owned)
   bool attached_mode = false;
+  // compact attach mode: [frames][pdfs] IEEE half bits + one offset per frame (not owned)
+  const uint16_t *h16 = nullptr;
+  const float *off = nullptr;
+  float scale = 1.0f;
 };
+
+namespace {
+// IEEE half -> float without relying on F16C: 1-5-10 bits, subnormals and inf/nan included
+inline float half_bits_to_float(uint16_t h) {
+  const uint32_t sign = static_cast<uint32_t>(h & 0x8000u) << 16;
+  uint32_t exp = (h >> 10) & 0x1fu, man = h & 0x3ffu, bits;
+  if (exp == 0) {
+    if (man == 0) {
+      bits = sign;
+    } else {
+      int e = -1;
+      do { man <<= 1; ++e; } while ((man & 0x400u) == 0);
+      bits = sign | static_cast<uint32_t>(127 - 15 - e) << 23 | (man & 0x3ffu) << 13;
+    }
+  } else if (exp == 31) {
+    bits = sign | 0x7f800000u | man << 13;
+  } else {
+    bits = sign | (exp + 127 - 15) << 23 | man << 13;
+  }
+  float f;
+  memcpy(&f, &bits, sizeof(f));
+  return f;
+}
+}  // namespace
 
 namespace {
 
@@ -297,6 +325,14 @@ void pk_decodable_attach(pk_decodable_t *self, AcousticModel *am, float *log_pro
   self->frames_ready = ready != nullptr ? 0 : frames;
 }
 
+void pk_decodable_attach_compact(pk_decodable_t *self, AcousticModel *am, const uint16_t *h16,
+                                 const float *off, int frames, float prob_scale, pkb_event *ready) {
+  pk_decodable_attach(self, am, nullptr, frames, ready);
+  self->lazy->h16 = h16;
+  self->lazy->off = off;
+  self->lazy->scale = prob_scale;
+}
+
 void pk_decodable_destroy(pk_decodable_t *self) {
   if (self->lazy == nullptr) {
     pk_matrix_destroy(&self->log_prob);
@@ -329,6 +365,12 @@ float pk_decodable_loglikelihood(pk_decodable_t *self, int frame, int trans_id) 
     }
   }
   const int pdf_id = self->am->TransitionIdToPdfId(trans_id);
+  if (self->lazy != nullptr && self->lazy->h16 != nullptr) {
+    // compact rows: the last step of the epilogue (offset, prob_scale) happens per look-up
+    const pkb_lazy_decodable *l = self->lazy;
+    return l->scale * (half_bits_to_float(l->h16[static_cast<size_t>(frame) * self->log_prob.nrow + pdf_id]) +
+                       l->off[frame]);
+  }
   return self->log_prob.data[static_cast<size_t>(frame) * self->log_prob.nrow + pdf_id];
 }
 

@@ -149,4 +149,12 @@ POCKETKALDI_EXPORT
 void pk_decodable_attach(pk_decodable_t *self, AcousticModel *am, float *log_prob, int frames,
                          pkb_event *ready);
 
+// Same over the compact output of a batch (pkb_batch_set_compact, include/pkb200.h): rows of IEEE
+// half bits plus one FP32 offset per frame; the look-up returns
+// prob_scale * (half(h16[frame][pdf]) + off[frame]), i.e. the tail of the GPU epilogue moves into
+// pk_decodable_loglikelihood and the rows cross PCIe at half the size.
+POCKETKALDI_EXPORT
+void pk_decodable_attach_compact(pk_decodable_t *self, AcousticModel *am, const uint16_t *h16,
+                                 const float *off, int frames, float prob_scale, pkb_event *ready);
+
 #endif  // PKB_SHIM_H_

@@ -42,6 +42,11 @@ extern "C" {
 #define PKB_PREC_BF16X3 1 /* split BF16 (hi+lo), 3 MMAs: FP32-class accuracy; parity mode */
 #define PKB_PREC_FP16 2   /* one FP16 MMA per product (11-bit significand, BF16 speed); operands
                              must stay below 65504 in magnitude                              */
+#define PKB_PREC_FP16X3 3 /* split FP16 (hi+lo), 3 MMAs: the most accurate mode (error ~2^-22)  */
+#define PKB_PREC_FP16C8 4 /* FP16 product + the two first-order correction terms through FP8 (E4M3)
+                             operands at twice the MMA rate: 2 MMA-equivalents per product,
+                             error ~2^-15. Meets the parity bar; the first layer (whose spliced
+                             input view has a 40-byte row pitch in FP8) runs as FP16X3        */
 
 /* ---- fixed front-end geometry (src/fbank.h:7-13, src/cmvn.h:10-11) -------- */
 #define PKB_FBANK_DIM 40

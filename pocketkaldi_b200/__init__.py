@@ -28,6 +28,8 @@ from .binding import (  # noqa: F401
     PREC_BF16,
     PREC_BF16X3,
     PREC_FP16,
+    PREC_FP16X3,
+    PREC_FP16C8,
     STAGE_FBANK,
     STAGE_CMVN,
     STAGE_NNET,

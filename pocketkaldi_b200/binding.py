@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(HERE, "libpkb200.so")
 CSRC = os.path.join(HERE, "csrc")
 
 PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2
+PREC_FP16X3, PREC_FP16C8 = 3, 4
 STAGE_FBANK, STAGE_CMVN, STAGE_NNET, STAGE_ALL = 1, 2, 4, 7
 STAGE_NO_FEATS = 8  # with STAGE_CMVN + a model: skip the FP32 copy of the CMVN features
 BUF_PCM, BUF_RAW, BUF_FEATS, BUF_LOGLIK = 0, 1, 2, 3

@@ -95,85 +95,49 @@ __device__ __forceinline__ void cmvn_frame(const CmvnChain &c, int t, int i, flo
   }
 }
 
-// Frames [tb, te) of one phase. The chain is a few dependent operations per frame; what has to be
-// hidden is the load latency, so the loads of the next group of kCmvnUnroll frames are issued
-// before the current group is consumed (two register sets). Whole groups run without
-// per-frame bounds checks; the last, partial group is predicated. `wide` is the chain's sticky
-// "a value outside the exact-FP32 range was seen" flag.
-template <bool kSub, bool kAlpha, int kPlanes, bool kFp16, bool kOut>
-__device__ __forceinline__ void cmvn_phase(const CmvnChain &c, int tb, int te, float &stat, bool &wide,
-                                           const float *s_alpha, const float *s_scale, float scale_full) {
-  if (tb >= te) return;
-  float xa[kCmvnUnroll], pa[kCmvnUnroll], xb[kCmvnUnroll], pb[kCmvnUnroll];
-  auto load = [&](int t0, float (&xv)[kCmvnUnroll], float (&xp)[kCmvnUnroll]) {
-    const bool whole = t0 + kCmvnUnroll <= te;
-    const float *px = c.x + static_cast<int64_t>(t0) * kMel;
-#pragma unroll
-    for (int i = 0; i < kCmvnUnroll; ++i) {
-      const bool ok = whole || t0 + i < te;
-      xv[i] = ok ? px[i * kMel] : 0.0f;
-      xp[i] = (kSub && ok) ? px[(i - kCmvnWindow) * kMel] : 0.0f;
-    }
-  };
-  auto consume = [&](int t0, const float (&xv)[kCmvnUnroll], const float (&xp)[kCmvnUnroll]) {
-    // out-of-range values of the group make the chain wide before they are used; every x_old was
-    // an x of this chain 600 frames earlier, so it has been checked already
-    bool w = wide;
-#pragma unroll
-    for (int i = 0; i < kCmvnUnroll; ++i) w = w || cmvn_out_of_range(xv[i]);
-    wide = w;
-    const bool whole = t0 + kCmvnUnroll <= te;
-    float al[kCmvnUnroll], sc[kCmvnUnroll];
-#pragma unroll
-    for (int i = 0; i < kCmvnUnroll; ++i) {
-      // the tables have 600 entries and the phases that use them end at t = 599 / 600
-      const int ti = min(t0 + i, kCmvnWindow - 1);
-      al[i] = kAlpha ? s_alpha[ti] : 0.0f;
-      sc[i] = kSub ? scale_full : s_scale[ti];
-    }
-    if (kSub && w) {
-#pragma unroll
-      for (int i = 0; i < kCmvnUnroll; ++i)
-        if (whole || t0 + i < te)
-          cmvn_frame<kSub, kAlpha, true, kPlanes, kFp16, kOut>(c, t0, i, xv[i], xp[i], stat, al[i], sc[i]);
-    } else if (whole) {
-#pragma unroll
-      for (int i = 0; i < kCmvnUnroll; ++i)
-        cmvn_frame<kSub, kAlpha, false, kPlanes, kFp16, kOut>(c, t0, i, xv[i], xp[i], stat, al[i], sc[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < kCmvnUnroll; ++i)
-        if (t0 + i < te)
-          cmvn_frame<kSub, kAlpha, false, kPlanes, kFp16, kOut>(c, t0, i, xv[i], xp[i], stat, al[i], sc[i]);
-    }
-  };
-  load(tb, xa, pa);
-  for (int t0 = tb; t0 < te; t0 += 2 * kCmvnUnroll) {
-    load(t0 + kCmvnUnroll, xb, pb);
-    consume(t0, xa, pa);
-    load(t0 + 2 * kCmvnUnroll, xa, pa);
-    consume(t0 + kCmvnUnroll, xb, pb);
-  }
+// cp.async: 4 bytes global -> shared without passing through a register; completion is tracked
+// per thread in commit groups.
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
-// One thread per chain, up to 160 threads (four utterances) per block; at most 4 blocks per SM
-// (the two prefetch register sets must not spill).
-template <int kPlanes, bool kFp16, bool kOut>
-__global__ void __launch_bounds__(160, 4)
+constexpr int kCmvnGroups = 4;                       // groups of kCmvnUnroll frames in flight per chain
+constexpr int kCmvnRing = kCmvnGroups * kCmvnUnroll;  // 32 frames
+
+// One thread per chain (utterance, dim). The recurrence is a handful of dependent FP32
+// operations per frame, so what limits the kernel is how many bytes each chain keeps in flight:
+// every thread streams its x[t] and x[t - 600] through a private shared-memory ring with
+// cp.async, three groups (24 frames) ahead of the group it is consuming, and no thread ever
+// reads another thread's slots (no block-level synchronisation in the loop).
+// Frames t < 600 fill the window (global stats blended in through the alpha / scale tables, which
+// hold alpha = 0 at t = 599); frames t >= 600 slide it. 600 is a multiple of the group size, so a
+// group lies in one phase.
+template <int kPlanes, bool kFp16, bool kOut, int kBlock>
+__global__ void __launch_bounds__(kBlock, kBlock == 160 ? 5 : 16)
 cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off,
             const int32_t *__restrict__ num_frames, int n_utts,
             const float *__restrict__ tab /* alpha[600], scale[600], global[41] */,
             float *__restrict__ out, __nv_bfloat16 *__restrict__ p_hi,
             __nv_bfloat16 *__restrict__ p_lo, const int64_t *__restrict__ pad_off, int left,
             int right, int dim_pad) {
+  static_assert(kCmvnWindow % kCmvnUnroll == 0, "a group must not straddle the two phases");
   __shared__ float s_alpha[kCmvnWindow];
   __shared__ float s_scale[kCmvnWindow];
-  for (int i = threadIdx.x; i < kCmvnWindow; i += blockDim.x) {
+  extern __shared__ float s_ring[];  // [2][kCmvnRing][kBlock]: x, then x_old
+  for (int i = threadIdx.x; i < kCmvnWindow; i += kBlock) {
     s_alpha[i] = tab[i];
     s_scale[i] = tab[kCmvnWindow + i];
   }
   __syncthreads();
-  const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
   const int u = static_cast<int>(g / kMel);
   const int d = static_cast<int>(g % kMel);
   if (u >= n_utts) return;
@@ -187,15 +151,75 @@ cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off
   c.ph = kPlanes >= 1 ? p_hi + (pad_off[u] + left) * dim_pad + d : nullptr;
   c.pl = kPlanes == 2 ? p_lo + (pad_off[u] + left) * dim_pad + d : nullptr;
 
-  // three phases instead of per-frame tests on t: filling window with global smoothing
-  // (t < 599), the frame that completes the window (t = 599: no smoothing, nothing leaves yet),
-  // and the full sliding window (t >= 600: scale is the constant 1/600)
+  float *rx = s_ring + threadIdx.x;
+  float *ro = rx + kCmvnRing * kBlock;
+  const int T8 = T & ~(kCmvnUnroll - 1);  // whole groups run without per-frame bounds checks
+  // one commit group per call (possibly empty) keeps the wait count static
+  auto issue = [&](int t0) {
+    if (t0 < T8) {
+      const float *px = c.x + static_cast<int64_t>(t0) * kMel;
+      float *dx = rx + (t0 & (kCmvnRing - 1)) * kBlock;
+#pragma unroll
+      for (int i = 0; i < kCmvnUnroll; ++i) cp_async4(dx + i * kBlock, px + i * kMel);
+      if (t0 >= kCmvnWindow) {
+        float *dxo = ro + (t0 & (kCmvnRing - 1)) * kBlock;
+#pragma unroll
+        for (int i = 0; i < kCmvnUnroll; ++i) cp_async4(dxo + i * kBlock, px + (i - kCmvnWindow) * kMel);
+      }
+    }
+    cp_async_commit();
+  };
+
   float stat = 0.0f;
   bool wide = false;
   const float scale_full = s_scale[kCmvnWindow - 1];
-  cmvn_phase<false, true, kPlanes, kFp16, kOut>(c, 0, min(T, kCmvnWindow - 1), stat, wide, s_alpha, s_scale, scale_full);
-  cmvn_phase<false, false, kPlanes, kFp16, kOut>(c, kCmvnWindow - 1, min(T, kCmvnWindow), stat, wide, s_alpha, s_scale, scale_full);
-  cmvn_phase<true, false, kPlanes, kFp16, kOut>(c, kCmvnWindow, T, stat, wide, s_alpha, s_scale, scale_full);
+#pragma unroll
+  for (int k = 0; k < kCmvnGroups - 1; ++k) issue(k * kCmvnUnroll);
+  for (int t0 = 0; t0 < T8; t0 += kCmvnUnroll) {
+    issue(t0 + (kCmvnGroups - 1) * kCmvnUnroll);
+    cp_async_wait<kCmvnGroups - 1>();  // the group of t0 has landed
+    const float *gx = rx + (t0 & (kCmvnRing - 1)) * kBlock;
+    float xv[kCmvnUnroll];
+    bool w = wide;
+#pragma unroll
+    for (int i = 0; i < kCmvnUnroll; ++i) {
+      xv[i] = gx[i * kBlock];
+      w = w || cmvn_out_of_range(xv[i]);
+    }
+    wide = w;
+    if (t0 < kCmvnWindow) {
+      const float *pa = s_alpha + t0, *ps = s_scale + t0;
+#pragma unroll
+      for (int i = 0; i < kCmvnUnroll; ++i)
+        cmvn_frame<false, true, false, kPlanes, kFp16, kOut>(c, t0, i, xv[i], 0.0f, stat, pa[i], ps[i]);
+    } else {
+      const float *go = ro + (t0 & (kCmvnRing - 1)) * kBlock;
+      float xp[kCmvnUnroll];
+#pragma unroll
+      for (int i = 0; i < kCmvnUnroll; ++i) xp[i] = go[i * kBlock];
+      if (w) {
+#pragma unroll
+        for (int i = 0; i < kCmvnUnroll; ++i)
+          cmvn_frame<true, false, true, kPlanes, kFp16, kOut>(c, t0, i, xv[i], xp[i], stat, 0.0f, scale_full);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kCmvnUnroll; ++i)
+          cmvn_frame<true, false, false, kPlanes, kFp16, kOut>(c, t0, i, xv[i], xp[i], stat, 0.0f, scale_full);
+      }
+    }
+  }
+  // the last T % 8 frames, one at a time straight from global memory
+  for (int t = T8; t < T; ++t) {
+    const float x = c.x[static_cast<int64_t>(t) * kMel];
+    wide = wide || cmvn_out_of_range(x);
+    if (t < kCmvnWindow) {
+      cmvn_frame<false, true, false, kPlanes, kFp16, kOut>(c, t, 0, x, 0.0f, stat, s_alpha[t], s_scale[t]);
+    } else {
+      const float xo = c.x[static_cast<int64_t>(t - kCmvnWindow) * kMel];
+      if (wide) cmvn_frame<true, false, true, kPlanes, kFp16, kOut>(c, t, 0, x, xo, stat, 0.0f, scale_full);
+      else cmvn_frame<true, false, false, kPlanes, kFp16, kOut>(c, t, 0, x, xo, stat, 0.0f, scale_full);
+    }
+  }
 
   // replicated edge rows of the padded planes (AcousticModel::SpliceFeats clamps at the
   // utterance edges, src/am.cc:65-88): copies of this thread's own first / last element
@@ -298,23 +322,30 @@ int launch_cmvn(Ctx *c, const float *d_raw, const BatchMeta &m, float *d_out,
   // single-warp blocks spread over all SM sub-partitions instead of a few 5-warp blocks
   const int block = threads >= static_cast<int64_t>(c->sm_count) * 4 * 160 ? 160 : 32;
   const int grid = static_cast<int>((threads + block - 1) / block);
+  // per-thread rings: x and x_old, kCmvnRing frames each
+  size_t dyn_smem = static_cast<size_t>(2) * kCmvnRing * block * sizeof(float);
   // PKB_CMVN_BLOCKS_PER_SM=n (tuning knob): caps residency with unused dynamic shared memory
   static const int max_blocks = getenv("PKB_CMVN_BLOCKS_PER_SM") ? atoi(getenv("PKB_CMVN_BLOCKS_PER_SM")) : 0;
-  const size_t dyn_smem = max_blocks > 0 ? std::max<size_t>(0, (220 * 1024) / max_blocks - 6 * 1024) : 0;
+  if (max_blocks > 0) dyn_smem = std::max<size_t>(dyn_smem, (220 * 1024) / max_blocks - 6 * 1024);
   LaunchScope scope(c, PKB_KERNEL_CMVN);
   __nv_bfloat16 *hi = planes ? planes->hi : nullptr, *lo = planes ? planes->lo : nullptr;
   const int n_planes = hi ? (lo ? 2 : 1) : 0;
   const bool fp16 = planes && planes->fp16;
   PKB_REQUIRE(!planes || planes->dim_pad == kMel, "cmvn: operand planes must have a row pitch of %d elements", kMel);
-#define PKB_CMVN_LAUNCH2(PL, FP, OUT)                                                                \
-  do {                                                                                               \
-    if (dyn_smem > 0)                                                                                \
-      cudaFuncSetAttribute(cmvn_kernel<PL, FP, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                           static_cast<int>(dyn_smem));                                              \
-    cmvn_kernel<PL, FP, OUT><<<grid, block, dyn_smem, c->stream>>>(                                  \
-        d_raw, m.d_frame_off, m.d_num_frames, m.n_utts, c->cmvn_tab.as<float>(), d_out, hi, lo,      \
-        planes ? planes->d_pad_off : nullptr, planes ? planes->left : 0, planes ? planes->right : 0, \
-        planes ? planes->dim_pad : 0);                                                               \
+#define PKB_CMVN_LAUNCH3(PL, FP, OUT, BLK)                                                               \
+  do {                                                                                                  \
+    if (dyn_smem > 40 * 1024)                                                                           \
+      cudaFuncSetAttribute(cmvn_kernel<PL, FP, OUT, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                           static_cast<int>(dyn_smem));                                                 \
+    cmvn_kernel<PL, FP, OUT, BLK><<<grid, BLK, dyn_smem, c->stream>>>(                                  \
+        d_raw, m.d_frame_off, m.d_num_frames, m.n_utts, c->cmvn_tab.as<float>(), d_out, hi, lo,         \
+        planes ? planes->d_pad_off : nullptr, planes ? planes->left : 0, planes ? planes->right : 0,    \
+        planes ? planes->dim_pad : 0);                                                                  \
+  } while (0)
+#define PKB_CMVN_LAUNCH2(PL, FP, OUT)                    \
+  do {                                                   \
+    if (block == 160) PKB_CMVN_LAUNCH3(PL, FP, OUT, 160); \
+    else PKB_CMVN_LAUNCH3(PL, FP, OUT, 32);               \
   } while (0)
 #define PKB_CMVN_LAUNCH(PL, FP)                  \
   do {                                           \
@@ -327,6 +358,7 @@ int launch_cmvn(Ctx *c, const float *d_raw, const BatchMeta &m, float *d_out,
   else if (n_planes == 1 && fp16) PKB_CMVN_LAUNCH(1, true);
   else if (n_planes == 2 && !fp16) PKB_CMVN_LAUNCH(2, false);
   else PKB_CMVN_LAUNCH(2, true);
+#undef PKB_CMVN_LAUNCH3
 #undef PKB_CMVN_LAUNCH2
 #undef PKB_CMVN_LAUNCH
   PKB_CUDA(cudaGetLastError());

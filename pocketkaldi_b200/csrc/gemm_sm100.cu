@@ -17,9 +17,18 @@
 // schedule, see get_tile). Hidden stages (and the BF16X3 output stage) run as CTA pairs
 // (cta_group::2): one 256-row MMA tile per cluster of two, each CTA loading half of the W tile.
 //
-// BF16X3: every operand is carried as two BF16 planes (hi, lo = bf16(x - hi)) and
+// BF16X3 / FP16X3: every operand is carried as two 16-bit planes (hi, lo = rn16(x - hi)) and
 // each K step issues hi*hi + lo*hi + hi*lo into the same accumulator, which brings
-// the product error down to ~2^-16 relative (FP32-class for this workload).
+// the product error down to ~2^-16 (2^-22) relative (FP32-class for this workload).
+//
+// FP16C8 (operand mode 3): the same first-order correction at two thirds of the tensor work.
+// The two cross terms only need ~4 bits because they are 2^-11 of the product, so they are
+// carried as FP8 (E4M3) planes and run at twice the FP16 MMA rate:
+//   acc = [ e4m3(a_lo * 2^11) * e4m3(W16 * 2^4)  +  e4m3(a16 * 2^2) * e4m3(W_lo * 2^13) ]   (kind::f8f6f4)
+//   acc = a16 * W16 + acc * 2^-15                                  (first kind::f16 MMA: scale-input-d)
+// i.e. all correction k-blocks of a tile are accumulated first at 2^15 times the final scale and
+// the first main MMA folds them in. One smem slot holds either a 64-wide FP16 k-block or a
+// 128-wide FP8 k-block (same bytes, same 128-byte swizzle, same descriptor advance).
 
 #include <stdlib.h>
 
@@ -51,10 +60,15 @@ constexpr int kMainThreads = 128;   // warps 0-3: TMA producer, MMA issuer, TMEM
 #ifndef PKB_FINAL_TEAMS
 #define PKB_FINAL_TEAMS 2
 #endif
+// `planes` is the operand mode of the main loop: 1 = one 16-bit plane, 2 = hi + lo planes (three
+// MMAs per product), 3 = FP16 + FP8 corrections (two MMA-equivalents per product).
 constexpr int epi_teams(bool final, int planes) { return final ? PKB_FINAL_TEAMS : (planes == 1 ? PKB_HID_TEAMS : 1); }
-constexpr int team_warps(bool final, int planes) { return final ? 16 / PKB_FINAL_TEAMS : (planes == 1 ? PKB_HID_WARPS : 4); }
+constexpr int team_warps(bool final, int planes) { return final ? 16 / PKB_FINAL_TEAMS : (planes == 2 ? 4 : PKB_HID_WARPS); }
 constexpr int epi_warps(bool final, int planes) { return epi_teams(final, planes) * team_warps(final, planes); }
 constexpr int num_threads(bool final, int planes) { return kMainThreads + 32 * epi_warps(final, planes); }
+// bytes of epilogue staging per warp of a hidden stage: one 32 x 128-byte tile per 16-bit output
+// plane, or the FP16 tile plus two 32 x 64-byte FP8 tiles
+constexpr uint32_t hid_stage_bytes(int planes, bool out8) { return (out8 || planes == 2) ? 8192u : 4096u; }
 constexpr int kMaxStages = 8;
 // clock64 probes of the pipeline phases (PKB_GEMM_DEBUG=1 prints them). Compiled in only with
 // -DPKB_GEMM_PROBES: even switched off at run time they cost the hidden stages cycles.
@@ -243,6 +257,54 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         : "memory");
 }
 
+// Same for FP8 (E4M3) operands: K = 32 per instruction.
+template <int CG>
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                        uint32_t idesc, uint32_t accumulate) {
+  if (CG == 1)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D = A * B + D * 2^-15 (scale-input-d of kind::f16): folds the FP8 correction sum, which was
+// accumulated at 2^15 times the final scale, into the first main MMA of a tile.
+template <int CG>
+__device__ __forceinline__ void umma_f16_fold15(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc) {
+  if (CG == 1)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 15;\n"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, 15;\n"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+}
+
 // Arrives on `bar` once all previously issued tcgen05.mma of this thread finished; for a CTA
 // pair the arrival is multicast to the barrier at the same offset in both CTAs.
 template <int CG>
@@ -344,19 +406,31 @@ __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
+// two floats -> two E4M3 bytes (a in the low byte), round to nearest, saturating
+__device__ __forceinline__ uint32_t pack_e4m3x2(float a, float b) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  return pack_e4m3x2(a, b) | (pack_e4m3x2(c, d) << 16);
+}
+
 struct SmemLayout {
   uint32_t stage_bytes, a_plane, w_plane, stages, epi_off, epi_bytes, bar_off, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool final, int cg) {
+__host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool final, int cg, bool out8) {
   SmemLayout L;
   L.a_plane = kBlockM * kBlockK * 2;
   L.w_plane = (block_n / cg) * kBlockK * 2;  // a CTA pair splits the W tile
-  L.stage_bytes = planes * (L.a_plane + L.w_plane);
+  // operand mode 3 streams one plane pair per slot (FP8 x FP8 or FP16 x FP16)
+  L.stage_bytes = (planes == 2 ? 2 : 1) * (L.a_plane + L.w_plane);
   // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
   // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch per team
   // (and per row one more float for the compact mode's max(z - log_prior))
-  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 3 * 128 * 8 + 3 * 128 * 4 : epi_warps(false, planes) * planes * 4096;
+  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 3 * 128 * 8 + 3 * 128 * 4
+                      : epi_warps(false, planes) * hid_stage_bytes(planes, out8);
   uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */ - L.epi_bytes;
   L.stages = avail / L.stage_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
@@ -394,13 +468,19 @@ __device__ __forceinline__ bool get_tile(const GemmParams &p, int it, uint32_t r
   return mu < m_units;
 }
 
-template <int BN, int PLANES, bool FINAL, int CG>
+// Operand maps. PLANES 1/2: a_hi (a_lo) x w_hi (w_lo) 16-bit planes. PLANES 3 (FP16C8):
+//   a_hi = a16, a_lo = e4m3(a_lo * 2^11), a_x = e4m3(a16 * 2^2);  w_hi = W16, w_lo = e4m3(W_lo * 2^13),
+//   w_x = e4m3(W16 * 2^4); correction phase A = a_lo x w_x, phase B = a_x x w_lo, main = a_hi x w_hi.
+// OUT8 (hidden stages only): the epilogue writes the FP16C8 operand triple of the next stage.
+template <int BN, int PLANES, bool FINAL, int CG, bool OUT8>
 __global__ void __launch_bounds__(num_threads(FINAL, PLANES), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-            const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_a_x,
+            const __grid_constant__ CUtensorMap tm_w_x, const GemmParams p) {
+  static_assert(!(FINAL && OUT8), "the output stage writes FP32 / compact rows");
   extern __shared__ uint8_t smem_raw[];
-  const SmemLayout L = smem_layout(BN, PLANES, FINAL, CG);
+  const SmemLayout L = smem_layout(BN, PLANES, FINAL, CG, OUT8);
   uint8_t *smem = reinterpret_cast<uint8_t *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
@@ -419,9 +499,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (FINAL) tma_prefetch_desc(&tm_out);
     tma_prefetch_desc(&tm_a_hi);
     tma_prefetch_desc(&tm_w_hi);
-    if (PLANES == 2) {
+    if (PLANES >= 2) {
       tma_prefetch_desc(&tm_a_lo);
       tma_prefetch_desc(&tm_w_lo);
+    }
+    if (PLANES == 3) {
+      tma_prefetch_desc(&tm_a_x);
+      tma_prefetch_desc(&tm_w_x);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -452,13 +536,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       for (int it = 0; get_tile<CG>(p, it, cta_rank, m_blk, n_blk); ++it) {
         const int m0 = m_blk * kBlockM;
         const int n0 = n_blk * BN + static_cast<int>(cta_rank) * (BN / CG);  // this CTA's W rows
+        if (PLANES == 3) {
+          // FP8 correction phases: 128-element (= 128-byte) k-blocks, A: a_lo8 x W_hi8, B: a_hi8 x W_lo8
+          for (int kb = 0; kb < 2 * p.num_kb8; ++kb) {
+            const bool phase_b = kb >= p.num_kb8;
+            const int k0 = (phase_b ? kb - p.num_kb8 : kb) * 128;
+            const CUtensorMap *ma = phase_b ? &tm_a_x : &tm_a_lo;
+            const CUtensorMap *mw = phase_b ? &tm_w_lo : &tm_w_x;
+            mbar_wait<64>(&empty[s], ph ^ 1);
+            uint8_t *st = smem + s * L.stage_bytes;
+            if (CG == 1) {
+              mbar_expect_tx(&full[s], L.stage_bytes);
+              tma_load_2d(st, ma, &full[s], k0, m0);
+              tma_load_2d(st + L.a_plane, mw, &full[s], k0, n0);
+            } else {
+              if (leader) mbar_expect_tx(&full[s], 2 * L.stage_bytes);
+              tma_load_2d_pair(st, ma, &full[s], k0, m0);
+              tma_load_2d_pair(st + L.a_plane, mw, &full[s], k0, n0);
+            }
+            if (++s == S) { s = 0; ph ^= 1; }
+          }
+        }
+        constexpr int kWOff = PLANES == 2 ? 2 : 1;  // W planes follow the A planes of a slot
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait<64>(&empty[s], ph ^ 1);
           uint8_t *st = smem + s * L.stage_bytes;
           if (CG == 1) {
             mbar_expect_tx(&full[s], L.stage_bytes);
             tma_load_2d(st, &tm_a_hi, &full[s], kb * kBlockK, m0);
-            tma_load_2d(st + PLANES * L.a_plane, &tm_w_hi, &full[s], kb * kBlockK, n0);
+            tma_load_2d(st + kWOff * L.a_plane, &tm_w_hi, &full[s], kb * kBlockK, n0);
             if (PLANES == 2) {
               tma_load_2d(st + L.a_plane, &tm_a_lo, &full[s], kb * kBlockK, m0);
               tma_load_2d(st + 2 * L.a_plane + L.w_plane, &tm_w_lo, &full[s], kb * kBlockK, n0);
@@ -467,7 +573,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             // the leader's barrier collects the bytes of both CTAs' loads
             if (leader) mbar_expect_tx(&full[s], 2 * L.stage_bytes);
             tma_load_2d_pair(st, &tm_a_hi, &full[s], kb * kBlockK, m0);
-            tma_load_2d_pair(st + PLANES * L.a_plane, &tm_w_hi, &full[s], kb * kBlockK, n0);
+            tma_load_2d_pair(st + kWOff * L.a_plane, &tm_w_hi, &full[s], kb * kBlockK, n0);
             if (PLANES == 2) {
               tma_load_2d_pair(st + L.a_plane, &tm_a_lo, &full[s], kb * kBlockK, m0);
               tma_load_2d_pair(st + 2 * L.a_plane + L.w_plane, &tm_w_lo, &full[s], kb * kBlockK, n0);
@@ -491,19 +597,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         tc_fence_after();
         if (kProbes && p.dbg != nullptr) p.dbg[static_cast<size_t>(blockIdx.x) * 16 + 6] += clock64() - tw0;
         const uint32_t d_tmem = tmem_base + as * BN;
+        if (PLANES == 3) {
+          // correction sum first (FP8, K = 32 per instruction = the same 32-byte descriptor step)
+          const uint32_t idesc8 = make_idesc(kBlockM * CG, BN, 0u);  // E4M3 is format 0 of kind::f8f6f4
+          for (int kb = 0; kb < 2 * p.num_kb8; ++kb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * L.stage_bytes);
+            const uint64_t a8 = make_smem_desc(sa);
+            const uint64_t w8 = make_smem_desc(sa + L.a_plane);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = static_cast<uint64_t>((k * 32) >> 4);
+              umma_f8<CG>(d_tmem, a8 + adv, w8 + adv, idesc8, (kb | k) != 0);
+            }
+            umma_commit<CG>(&empty[s]);
+            if (++s == S) { s = 0; ph ^= 1; }
+          }
+        }
+        constexpr int kWOff = PLANES == 2 ? 2 : 1;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           if (kProbes && p.dbg != nullptr) tw0 = clock64();
           mbar_wait(&full[s], ph);
           tc_fence_after();
           if (kProbes && p.dbg != nullptr) tw_full += clock64() - tw0;
           const uint32_t sa = smem_u32(smem + s * L.stage_bytes);
-          const uint32_t sw = sa + PLANES * L.a_plane;
+          const uint32_t sw = sa + kWOff * L.a_plane;
           const uint64_t a_hi = make_smem_desc(sa);
           const uint64_t w_hi = make_smem_desc(sw);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-            umma_bf16<CG>(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+            if (PLANES == 3 && k == 0) {
+              // the tile's first main MMA folds the correction sum in (acc * 2^-15 + a16 * W16)
+              if (kb == 0) umma_f16_fold15<CG>(d_tmem, a_hi + adv, w_hi + adv, idesc);
+              else umma_bf16<CG>(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+            } else {
+              umma_bf16<CG>(d_tmem, a_hi + adv, w_hi + adv, idesc, PLANES == 3 ? 1u : ((kb | k) != 0));
+            }
           }
           if (PLANES == 2) {
             const uint64_t a_lo = make_smem_desc(sa + L.a_plane);
@@ -536,7 +667,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     // per-warp staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7);
     // rows are written by their owner lane and read back 4 rows per instruction so that
     // every global store covers whole 128-byte lines
-    uint8_t *stg = smem + L.epi_off + (FINAL ? (warp - 4) * 4096 : (warp - 4) * (PLANES * 4096));
+    uint8_t *stg = smem + L.epi_off + (warp - 4) * (FINAL ? 4096u : hid_stage_bytes(PLANES, OUT8));
+    // OUT8: the two FP8 tiles (32 rows x 64 bytes, 16-byte chunks XOR-swizzled by (row >> 1) & 3)
+    // follow the FP16 tile
+    const uint32_t stg8_w = smem_u32(stg) + 4096 + lane * 64;
     const uint32_t stg_w = smem_u32(stg) + lane * 128;          // this lane's row
     // grouped schedule: this CTA's column tile never changes, keep its bias / log-prior in smem
     float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + 16 * 4096);
@@ -567,6 +701,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           ss += p.in_sumsq[static_cast<size_t>(row) * p.in_sumsq_tiles + i];
         rs = sqrtf(p.in_dim / ss);  // NormalizeLayer: no floor (src/nnet.cc:71-73)
       }
+      if (PLANES == 3) rs *= p.acc_scale;  // FP16C8 weights are stored times a power of two
 
       long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tkm = 0;
       const bool dbg_on = kProbes && p.dbg != nullptr && warp == 4 && lane == 0;  // team 0
@@ -615,12 +750,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               st_shared_v4(stg_w + (((h * 4 + j) ^ (lane & 7)) << 4), hi[4 * j], hi[4 * j + 1],
                            hi[4 * j + 2], hi[4 * j + 3]);
             if (dbg_on) tkm += clock64() - tk2;
-            if (PLANES == 2) {
+            if (OUT8) {
+              // next stage's FP8 correction operands: e4m3((z - fp16(z)) * 2^11) and e4m3(fp16(z) * 2^2)
+              uint32_t l8[8], h8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float f[4], r[4];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const __half2 hh = *reinterpret_cast<const __half2 *>(&hi[2 * i + e]);
+                  f[2 * e] = __low2float(hh);
+                  f[2 * e + 1] = __high2float(hh);
+                  r[2 * e] = (z[4 * i + 2 * e] - f[2 * e]) * 2048.0f;
+                  r[2 * e + 1] = (z[4 * i + 2 * e + 1] - f[2 * e + 1]) * 2048.0f;
+                }
+                l8[i] = pack_e4m3x4(r[0], r[1], r[2], r[3]);
+                h8[i] = pack_e4m3x4(f[0] * 4.0f, f[1] * 4.0f, f[2] * 4.0f, f[3] * 4.0f);
+              }
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t o = ((h * 2 + j) ^ ((lane >> 1) & 3)) << 4;
+                st_shared_v4(stg8_w + o, l8[4 * j], l8[4 * j + 1], l8[4 * j + 2], l8[4 * j + 3]);
+                st_shared_v4(stg8_w + 2048 + o, h8[4 * j], h8[4 * j + 1], h8[4 * j + 2], h8[4 * j + 3]);
+              }
+            }
+            if (PLANES == 2 && !OUT8) {
               uint32_t lo[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const __nv_bfloat162 hh = *reinterpret_cast<__nv_bfloat162 *>(&hi[i]);
-                lo[i] = pack_bf16(z[2 * i] - __low2float(hh), z[2 * i + 1] - __high2float(hh));
+                if (p.fp16) {
+                  const __half2 hh = *reinterpret_cast<const __half2 *>(&hi[i]);
+                  lo[i] = pack_f16(z[2 * i] - __low2float(hh), z[2 * i + 1] - __high2float(hh));
+                } else {
+                  const __nv_bfloat162 hh = *reinterpret_cast<__nv_bfloat162 *>(&hi[i]);
+                  lo[i] = pack_bf16(z[2 * i] - __low2float(hh), z[2 * i + 1] - __high2float(hh));
+                }
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j)
@@ -637,7 +801,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               const uint32_t src = smem_u32(stg) + rr * 128 + ((t_chunk ^ (rr & 7)) << 4);
               const size_t off = static_cast<size_t>(wrow0 + rr) * p.ld_out + col0 + t_chunk * 8;
               *reinterpret_cast<uint4 *>(p.out_hi + off) = ld_shared_v4(src);
-              if (PLANES == 2) *reinterpret_cast<uint4 *>(p.out_lo + off) = ld_shared_v4(src + 4096);
+              if (PLANES == 2 && !OUT8) *reinterpret_cast<uint4 *>(p.out_lo + off) = ld_shared_v4(src + 4096);
+            }
+          }
+          if (OUT8) {
+            // 64-byte rows: four lanes per row, eight rows per instruction
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + (lane >> 2), ch = lane & 3;
+              if (wrow0 + rr < p.M) {
+                const uint32_t src = smem_u32(stg) + 4096 + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4);
+                const size_t off = static_cast<size_t>(wrow0 + rr) * p.ld_out + col0 + ch * 16;
+                *reinterpret_cast<uint4 *>(p.out8_lo + off) = ld_shared_v4(src);
+                *reinterpret_cast<uint4 *>(p.out8_hi + off) = ld_shared_v4(src + 2048);
+              }
             }
           }
           __syncwarp();
@@ -955,9 +1132,10 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, int PLANES, bool FINAL, int CG>
-int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const CUtensorMap *w_hi,
-               const CUtensorMap *w_lo, const GemmParams &p) {
+template <int BN, int PLANES, bool FINAL, int CG, bool OUT8>
+int launch_one(Ctx *c, const GemmMaps &mp, const GemmParams &p) {
+  const CUtensorMap *a_hi = mp.a_hi, *a_lo = mp.a_lo, *w_hi = mp.w_hi, *w_lo = mp.w_lo;
+  const CUtensorMap *a_x = PLANES == 3 ? mp.a_x : mp.a_hi, *w_x = PLANES == 3 ? mp.w_x : mp.w_hi;
   // FP32 output map of the final stage (hidden stages pass a dummy copy of the A map)
   CUtensorMap out_map = *a_hi;
   if (FINAL && p.final_mode == 3) {
@@ -965,8 +1143,8 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
   } else if (FINAL && (p.ld_f32 & 3) == 0) {
     PKB_TRY(make_output_map(&out_map, p.out_f32, p.N_valid, p.M));
   }
-  const SmemLayout L = smem_layout(BN, PLANES, FINAL, CG);
-  auto kern = gemm_kernel<BN, PLANES, FINAL, CG>;
+  const SmemLayout L = smem_layout(BN, PLANES, FINAL, CG, OUT8);
+  auto kern = gemm_kernel<BN, PLANES, FINAL, CG, OUT8>;
   PKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   GemmParams pp = p;
   pp.m_tiles = (p.M + kBlockM - 1) / kBlockM;
@@ -1002,8 +1180,8 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
     // for each other: a cooperative launch guarantees that all CTAs are co-resident
     // (+1: a CTA pair may work on one row block past the end of the matrix)
     PKB_CUDA(cudaMemsetAsync(p.tile_done, 0, sizeof(int) * ((p.M + kBlockM - 1) / kBlockM + 1), c->stream));
-    CUtensorMap m0 = *a_hi, m1 = *a_lo, m2 = *w_hi, m3 = *w_lo;
-    void *args[] = {&m0, &m1, &m2, &m3, &out_map, &pp};
+    CUtensorMap m0 = *a_hi, m1 = *a_lo, m2 = *w_hi, m3 = *w_lo, m5 = *a_x, m6 = *w_x;
+    void *args[] = {&m0, &m1, &m2, &m3, &out_map, &m5, &m6, &pp};
     if (CG == 1) {
       PKB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid),
                                            dim3(num_threads(FINAL, PLANES)), args, L.total, c->stream));
@@ -1026,9 +1204,10 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
       // grid (<= one CTA per SM) holds without the attribute.
       static const bool tool_attached = getenv("CUDA_INJECTION64_PATH") != nullptr ||
                                         getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
+                                        getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr ||
                                         getenv("PKB_NO_COOP_CLUSTER") != nullptr;
       cfg.numAttrs = tool_attached ? 1 : 2;
-      PKB_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, m2, m3, out_map, pp));
+      PKB_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, m2, m3, out_map, m5, m6, pp));
     }
   } else if (CG == 2) {
     cudaLaunchConfig_t cfg{};
@@ -1043,9 +1222,10 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PKB_CUDA(cudaLaunchKernelEx(&cfg, kern, *a_hi, *a_lo, *w_hi, *w_lo, out_map, pp));
+    PKB_CUDA(cudaLaunchKernelEx(&cfg, kern, *a_hi, *a_lo, *w_hi, *w_lo, out_map, *a_x, *w_x, pp));
   } else {
-    kern<<<grid, num_threads(FINAL, PLANES), L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, out_map, pp);
+    kern<<<grid, num_threads(FINAL, PLANES), L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, out_map, *a_x,
+                                                                   *w_x, pp);
   }
   PKB_CUDA(cudaGetLastError());
   }
@@ -1070,7 +1250,29 @@ int launch_one(Ctx *c, const CUtensorMap *a_hi, const CUtensorMap *a_lo, const C
 
 }  // namespace
 
-int gemm_max_smem_bytes(int block_n, int planes) { return smem_layout(block_n, planes, true, 1).total; }
+int gemm_max_smem_bytes(int block_n, int planes) { return smem_layout(block_n, planes, true, 1, false).total; }
+
+int make_tensor_map8(CUtensorMap *map, const void *base, uint64_t cols, uint64_t rows,
+                     uint64_t pitch_bytes, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return PKB_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (FP8) failed (CUresult %d) cols=%llu rows=%llu pitch=%llu", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_bytes);
+    return PKB_ERR_CUDA;
+  }
+  return PKB_OK;
+}
 
 int make_tensor_map(CUtensorMap *map, const void *base, uint64_t cols, uint64_t rows,
                     uint64_t pitch_bytes, uint32_t box_rows) {
@@ -1136,32 +1338,48 @@ int make_output_map16(CUtensorMap *map, const uint16_t *base, uint64_t cols, uin
   return PKB_OK;
 }
 
-int launch_gemm(Ctx *c, int block_n, int planes, bool final, int cta_group, const CUtensorMap *a_hi,
-                const CUtensorMap *a_lo, const CUtensorMap *w_hi, const CUtensorMap *w_lo,
-                const GemmParams &p) {
+int launch_gemm(Ctx *c, int block_n, int planes, bool final, int cta_group, bool out8,
+                const GemmMaps &maps, const GemmParams &p) {
   if (p.num_tiles <= 0) return PKB_OK;
-  if (planes == 1) { a_lo = a_hi; w_lo = w_hi; }
-  if (cta_group == 2) {
-    // CTA pairs: hidden stages with 256-wide tiles (the W maps must have box rows block_n / 2)
-    if (block_n == 256 && planes == 1 && !final) return launch_one<256, 1, false, 2>(c, a_hi, a_lo, w_hi, w_lo, p);
-    if (block_n == 256 && planes == 2 && !final) return launch_one<256, 2, false, 2>(c, a_hi, a_lo, w_hi, w_lo, p);
-    if (block_n == 256 && planes == 1 && final) return launch_one<256, 1, true, 2>(c, a_hi, a_lo, w_hi, w_lo, p);
-    if (block_n == 256 && planes == 2 && final) return launch_one<256, 2, true, 2>(c, a_hi, a_lo, w_hi, w_lo, p);
+  GemmMaps m = maps;
+  if (planes == 1) { m.a_lo = m.a_hi; m.w_lo = m.w_hi; }
+  if (out8 && (final || planes == 1)) {
+    set_error("launch_gemm: the FP8 operand triple is written by hidden stages of operand mode 2 or 3");
+    return PKB_ERR_INVALID;
+  }
+  if (cta_group == 2 && block_n != 256) {
     set_error("launch_gemm: cta_group 2 is built for block_n 256 only");
     return PKB_ERR_INVALID;
   }
-#define PKB_GEMM_CASE(BN, PL, FN) \
-  if (block_n == BN && planes == PL && final == FN) return launch_one<BN, PL, FN, 1>(c, a_hi, a_lo, w_hi, w_lo, p);
-  PKB_GEMM_CASE(128, 1, false)
-  PKB_GEMM_CASE(128, 1, true)
-  PKB_GEMM_CASE(128, 2, false)
-  PKB_GEMM_CASE(128, 2, true)
-  PKB_GEMM_CASE(256, 1, false)
-  PKB_GEMM_CASE(256, 1, true)
-  PKB_GEMM_CASE(256, 2, false)
-  PKB_GEMM_CASE(256, 2, true)
+#define PKB_GEMM_CASE(BN, PL, FN, CGV, O8) \
+  if (block_n == BN && planes == PL && final == FN && cta_group == CGV && out8 == O8) \
+    return launch_one<BN, PL, FN, CGV, O8>(c, m, p);
+  // CTA pairs (the W maps must have box rows block_n / 2)
+  PKB_GEMM_CASE(256, 1, false, 2, false)
+  PKB_GEMM_CASE(256, 2, false, 2, false)
+  PKB_GEMM_CASE(256, 1, true, 2, false)
+  PKB_GEMM_CASE(256, 2, true, 2, false)
+  PKB_GEMM_CASE(256, 2, false, 2, true)
+  PKB_GEMM_CASE(256, 3, false, 2, true)
+  PKB_GEMM_CASE(256, 3, true, 2, false)
+  // single CTAs
+  PKB_GEMM_CASE(128, 1, false, 1, false)
+  PKB_GEMM_CASE(128, 1, true, 1, false)
+  PKB_GEMM_CASE(128, 2, false, 1, false)
+  PKB_GEMM_CASE(128, 2, true, 1, false)
+  PKB_GEMM_CASE(256, 1, false, 1, false)
+  PKB_GEMM_CASE(256, 1, true, 1, false)
+  PKB_GEMM_CASE(256, 2, false, 1, false)
+  PKB_GEMM_CASE(256, 2, true, 1, false)
+  PKB_GEMM_CASE(128, 2, false, 1, true)
+  PKB_GEMM_CASE(256, 2, false, 1, true)
+  PKB_GEMM_CASE(128, 3, false, 1, true)
+  PKB_GEMM_CASE(256, 3, false, 1, true)
+  PKB_GEMM_CASE(128, 3, true, 1, false)
+  PKB_GEMM_CASE(256, 3, true, 1, false)
 #undef PKB_GEMM_CASE
-  set_error("launch_gemm: unsupported configuration block_n=%d planes=%d", block_n, planes);
+  set_error("launch_gemm: unsupported configuration block_n=%d planes=%d final=%d cta_group=%d out8=%d",
+            block_n, planes, final ? 1 : 0, cta_group, out8 ? 1 : 0);
   return PKB_ERR_INVALID;
 }
 

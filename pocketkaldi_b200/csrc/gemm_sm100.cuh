@@ -37,6 +37,9 @@ struct GemmParams {
   int m_tiles;         // set by the launcher
   int group_sched;     // set by the launcher: grouped schedule of the final softmax stage
   int num_kb;          // K_pad / kBlockK
+  int num_kb8;         // operand mode 3: 128-wide FP8 k-blocks per correction phase (ceil(K_pad / 128))
+  float acc_scale;     // operand mode 3: 2^-g, undoes the power-of-two scaling of the stored weights
+  uint8_t *out8_lo, *out8_hi;  // OUT8: [M][ld_out] E4M3 planes of the next stage's correction operands
   int N_valid;         // logical N (columns >= N_valid are padding)
   const float *bias;   // [N_pad], zero in the padding
   const float *in_sumsq;  // [M][in_sumsq_tiles] partial sums of squares, or nullptr
@@ -72,12 +75,22 @@ struct GemmParams {
 int make_tensor_map(CUtensorMap *map, const void *base, uint64_t cols, uint64_t rows,
                     uint64_t pitch_bytes, uint32_t box_rows);
 
-// block_n in {128, 256}; planes in {1 (BF16), 2 (BF16X3)}; final: FP32 output mode.
-// cta_group 2 (hidden stages, block_n 256): clusters of two CTAs share one 256-row tcgen05 tile,
+// Operand maps of one launch (see gemm_kernel): a_x / w_x are only read in operand mode 3.
+struct GemmMaps {
+  const CUtensorMap *a_hi, *a_lo, *a_x, *w_hi, *w_lo, *w_x;
+};
+
+// block_n in {128, 256}; planes (operand mode) in {1 one 16-bit plane, 2 hi + lo planes, 3 FP16 +
+// FP8 corrections}; final: FP32 / compact output mode; out8: a hidden stage that writes the
+// operand triple of a mode-3 successor.
+// cta_group 2 (block_n 256): clusters of two CTAs share one 256-row tcgen05 tile,
 // each loading half of the W tile (w maps with box rows block_n / 2).
-int launch_gemm(Ctx *c, int block_n, int planes, bool final, int cta_group, const CUtensorMap *a_hi,
-                const CUtensorMap *a_lo, const CUtensorMap *w_hi, const CUtensorMap *w_lo,
-                const GemmParams &p);
+int launch_gemm(Ctx *c, int block_n, int planes, bool final, int cta_group, bool out8,
+                const GemmMaps &maps, const GemmParams &p);
+
+// 2-D E4M3 K-major tensor map: inner dim `cols` bytes, box {128, box_rows}, 128-byte swizzle.
+int make_tensor_map8(CUtensorMap *map, const void *base, uint64_t cols, uint64_t rows,
+                     uint64_t pitch_bytes, uint32_t box_rows);
 
 // FP32 [rows][cols] output map for the final stage's TMA stores: box {32 cols, 32 rows},
 // 128-byte swizzle. Needs cols % 4 == 0 (16-byte row pitch).
@@ -91,7 +104,8 @@ int gemm_max_smem_bytes(int block_n, int planes);
 #ifndef PKB_HID_WARPS
 #define PKB_HID_WARPS 8
 #endif
-// Sum-of-squares partials one hidden tile writes per row (= epilogue warps per lane quadrant).
-inline int sumsq_parts(int planes) { return planes == 1 ? PKB_HID_WARPS / 4 : 1; }
+// Sum-of-squares partials one hidden tile writes per row (= epilogue warps per lane quadrant)
+// for operand mode `planes`.
+inline int sumsq_parts(int planes) { return planes == 2 ? 1 : PKB_HID_WARPS / 4; }
 
 }  // namespace pkb

@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_fp8.h>
+
 #include <algorithm>
 
 #include "nnet.cuh"
@@ -142,12 +144,73 @@ int pack_stage(Ctx *c, Stage *st, const float *W, const float *b, int out_dim, i
   return PKB_OK;
 }
 
+inline uint8_t to_e4m3(float v) {
+  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3));
+}
+
+// Operand mode 3 (FP16C8) planes of W[out][in]: W16 = fp16(W * 2^g) with max |W * 2^g| in [1, 2),
+// W_hi8 = e4m3(W16 * 2^4), W_lo8 = e4m3((W * 2^g - W16) * 2^13); see gemm_sm100.cu.
+int pack_stage_c8(Ctx *c, Stage *st, const float *W, const float *b, int out_dim, int in_dim) {
+  st->in_dim = in_dim;
+  st->out_dim = out_dim;
+  st->c8 = true;
+  st->k_pad = round_up(in_dim, kBlockK);
+  st->k_pad8 = round_up(in_dim, 128);
+  const int n128 = round_up(out_dim, 128), n256 = round_up(out_dim, 256);
+  st->block_n = (n256 * 100 <= n128 * 106) ? 256 : 128;
+  st->n_pad = st->block_n == 256 ? n256 : n128;
+  float wmax = 0.0f;
+  for (size_t i = 0; i < static_cast<size_t>(out_dim) * in_dim; ++i) wmax = std::max(wmax, fabsf(W[i]));
+  PKB_REQUIRE(std::isfinite(wmax), "linear layer: non-finite weight");
+  int e = 0;
+  if (wmax > 0.0f) frexpf(wmax, &e);  // wmax = m * 2^e, m in [0.5, 1)
+  st->w_exp = wmax > 0.0f ? 1 - e : 0; // W * 2^g has its maximum in [1, 2)
+  const float sg = ldexpf(1.0f, st->w_exp);
+  const size_t e16 = static_cast<size_t>(st->n_pad) * st->k_pad, e8 = static_cast<size_t>(st->n_pad) * st->k_pad8;
+  std::vector<__nv_bfloat16> hi(e16, operand_bits(0.0f, 1));
+  std::vector<uint8_t> h8(e8, 0), l8(e8, 0);
+  for (int o = 0; o < out_dim; ++o) {
+    const float *src = W + static_cast<size_t>(o) * in_dim;
+    for (int k = 0; k < in_dim; ++k) {
+      const float w = src[k] * sg;
+      const __nv_bfloat16 h = operand_bits(w, 1);
+      const float w16 = operand_value(h, 1);
+      hi[static_cast<size_t>(o) * st->k_pad + k] = h;
+      h8[static_cast<size_t>(o) * st->k_pad8 + k] = to_e4m3(w16 * 16.0f);
+      l8[static_cast<size_t>(o) * st->k_pad8 + k] = to_e4m3((w - w16) * 8192.0f);
+    }
+  }
+  std::vector<float> bias(st->n_pad, 0.0f);
+  memcpy(bias.data(), b, sizeof(float) * out_dim);
+  PKB_TRY(st->w_hi.ensure(e16 * 2));
+  PKB_CUDA(cudaMemcpy(st->w_hi.p, hi.data(), e16 * 2, cudaMemcpyHostToDevice));
+  PKB_TRY(st->w8_hi.ensure(e8));
+  PKB_CUDA(cudaMemcpy(st->w8_hi.p, h8.data(), e8, cudaMemcpyHostToDevice));
+  PKB_TRY(st->w8_lo.ensure(e8));
+  PKB_CUDA(cudaMemcpy(st->w8_lo.p, l8.data(), e8, cudaMemcpyHostToDevice));
+  PKB_TRY(st->bias.ensure(sizeof(float) * st->n_pad));
+  PKB_CUDA(cudaMemcpy(st->bias.p, bias.data(), sizeof(float) * st->n_pad, cudaMemcpyHostToDevice));
+  const uint64_t p16 = static_cast<uint64_t>(st->k_pad) * 2, p8 = static_cast<uint64_t>(st->k_pad8);
+  PKB_TRY(make_tensor_map(&st->tm_w_hi, st->w_hi.p, st->k_pad, st->n_pad, p16, st->block_n));
+  PKB_TRY(make_tensor_map(&st->tm_w_hi_half, st->w_hi.p, st->k_pad, st->n_pad, p16, st->block_n / 2));
+  st->tm_w_lo = st->tm_w_hi;
+  st->tm_w_lo_half = st->tm_w_hi_half;
+  PKB_TRY(make_tensor_map8(&st->tm_w8_hi, st->w8_hi.p, st->k_pad8, st->n_pad, p8, st->block_n));
+  PKB_TRY(make_tensor_map8(&st->tm_w8_hi_half, st->w8_hi.p, st->k_pad8, st->n_pad, p8, st->block_n / 2));
+  PKB_TRY(make_tensor_map8(&st->tm_w8_lo, st->w8_lo.p, st->k_pad8, st->n_pad, p8, st->block_n));
+  PKB_TRY(make_tensor_map8(&st->tm_w8_lo_half, st->w8_lo.p, st->k_pad8, st->n_pad, p8, st->block_n / 2));
+  (void)c;
+  return PKB_OK;
+}
+
 }  // namespace
 
 void Workspace::release() {
   for (int i = 0; i < 2; ++i) {
     act_hi[i].release();
     act_lo[i].release();
+    act8_lo[i].release();
+    act8_hi[i].release();
     sumsq[i].release();
   }
   lse_part.release();
@@ -173,7 +236,7 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
              const float *prior, int num_pdfs, int left, int right, const int32_t *tid2pdf,
              int n_tid2pdf, int precision, pkb_am **out) {
   PKB_REQUIRE(c && out, "pkb_am_create: NULL argument");
-  PKB_REQUIRE(precision == PKB_PREC_BF16 || precision == PKB_PREC_BF16X3 || precision == PKB_PREC_FP16,
+  PKB_REQUIRE(precision >= PKB_PREC_BF16 && precision <= PKB_PREC_FP16C8,
               "pkb_am_create: unknown precision %d", precision);
   PKB_REQUIRE(left >= 0 && right >= 0, "pkb_am_create: negative context");
   PKB_REQUIRE(n_layers > 0 && types, "pkb_am_create: empty layer list");
@@ -181,8 +244,9 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
   pkb_am *am = new pkb_am();
   am->c = c;
   am->precision = precision;
-  am->planes = precision == PKB_PREC_BF16X3 ? 2 : 1;
-  am->fp16 = precision == PKB_PREC_FP16 ? 1 : 0;
+  am->c8 = precision == PKB_PREC_FP16C8 ? 1 : 0;
+  am->planes = (precision == PKB_PREC_BF16X3 || precision == PKB_PREC_FP16X3 || am->c8) ? 2 : 1;
+  am->fp16 = (precision == PKB_PREC_FP16 || precision == PKB_PREC_FP16X3 || am->c8) ? 1 : 0;
   am->left = left;
   am->right = right;
   int rc = PKB_OK;
@@ -209,7 +273,9 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
     }
     am->stages.emplace_back();
     Stage &st = am->stages.back();
-    rc = pack_stage(c, &st, weights[lin], biases[lin], od, id, 0, 0, am->planes, am->fp16);
+    // FP16C8: stage 0 reads the 16-bit feature planes (three MMAs), later stages the FP8 triple
+    rc = (am->c8 && lin > 0) ? pack_stage_c8(c, &st, weights[lin], biases[lin], od, id)
+                             : pack_stage(c, &st, weights[lin], biases[lin], od, id, 0, 0, am->planes, am->fp16);
     if (rc != PKB_OK) break;
     if (lin == 0) {
       am->input_dim = id;
@@ -295,8 +361,13 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
   const int bufs = ns > 2 ? 2 : (ns > 1 ? 1 : 0);
   for (int i = 0; i < bufs; ++i) {
     PKB_TRY(ws->act_hi[i].ensure(static_cast<size_t>(rows) * max_hidden * 2));
-    if (am->planes == 2) PKB_TRY(ws->act_lo[i].ensure(static_cast<size_t>(rows) * max_hidden * 2));
-    PKB_TRY(ws->sumsq[i].ensure(static_cast<size_t>(rows) * max_tiles * sumsq_parts(am->planes) * sizeof(float)));
+    if (am->c8) {
+      PKB_TRY(ws->act8_lo[i].ensure(static_cast<size_t>(rows) * max_hidden));
+      PKB_TRY(ws->act8_hi[i].ensure(static_cast<size_t>(rows) * max_hidden));
+    } else if (am->planes == 2) {
+      PKB_TRY(ws->act_lo[i].ensure(static_cast<size_t>(rows) * max_hidden * 2));
+    }
+    PKB_TRY(ws->sumsq[i].ensure(static_cast<size_t>(rows) * max_tiles * 2 * sizeof(float)));
   }
   const Stage &last = am->stages.back();
   PKB_TRY(ws->lse_part.ensure(static_cast<size_t>((rows + kBlockM - 1) / kBlockM) * kBlockM *
@@ -308,7 +379,7 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
 }
 
 int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *first,
-                 FinalMode mode, float prob_scale, float *d_out, uint16_t *d_h16, float *d_off) {
+                 FinalMode mode_out, float prob_scale, float *d_out, uint16_t *d_h16, float *d_off) {
   Ctx *c = am->c;
   const int64_t rows = ws->rows;
   if (rows == 0) return PKB_OK;
@@ -319,12 +390,13 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
   const size_t ns = am->stages.size();
   // AcousticModel::Compute (src/am.cc:106-112) floors and takes the log of the nnet output, which
   // only means something for a SoftmaxLayer output; raw logits would silently differ from it
-  if ((mode == kFinalLoglik || mode == kFinalCompact) && !am->softmax_last) {
+  if ((mode_out == kFinalLoglik || mode_out == kFinalCompact) && !am->softmax_last) {
     set_error("log-likelihoods need a model whose last layer is a softmax (AcousticModel::Compute "
               "takes log(max(p, 1e-20)) of the nnet output)");
     return PKB_ERR_UNSUPPORTED;
   }
   const __nv_bfloat16 *a_hi = in.hi, *a_lo = in.lo;
+  const uint8_t *a8_lo = nullptr, *a8_hi = nullptr;  // FP16C8 operand triple of the current stage
   int a_cols = in.cols, a_pitch = in.pitch_elems;
   const float *in_sumsq = nullptr;
   int in_sumsq_tiles = 0;
@@ -333,12 +405,21 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
   for (size_t i = 0; i < ns; ++i) {
     const Stage &st = i == 0 ? *first : am->stages[i];
     const bool final = i + 1 == ns;
-    CUtensorMap tm_a_hi, tm_a_lo;
+    // operand mode of this stage and the form its epilogue has to produce for the next one
+    const int mode = st.c8 ? 3 : am->planes;
+    const bool out8 = !final && am->c8;
+    CUtensorMap tm_a_hi, tm_a_lo, tm_a_x;
     PKB_TRY(make_tensor_map(&tm_a_hi, a_hi, a_cols, rows, static_cast<uint64_t>(a_pitch) * 2, kBlockM));
-    if (am->planes == 2)
+    if (mode == 2) {
       PKB_TRY(make_tensor_map(&tm_a_lo, a_lo, a_cols, rows, static_cast<uint64_t>(a_pitch) * 2, kBlockM));
-    else
+      tm_a_x = tm_a_hi;
+    } else if (mode == 3) {
+      PKB_TRY(make_tensor_map8(&tm_a_lo, a8_lo, a_cols, rows, static_cast<uint64_t>(a_pitch), kBlockM));
+      PKB_TRY(make_tensor_map8(&tm_a_x, a8_hi, a_cols, rows, static_cast<uint64_t>(a_pitch), kBlockM));
+    } else {
       tm_a_lo = tm_a_hi;
+      tm_a_x = tm_a_hi;
+    }
     GemmParams p{};
     p.M = static_cast<int>(rows);
     p.n_tiles_n = st.n_pad / st.block_n;
@@ -346,6 +427,8 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
     PKB_REQUIRE(tiles <= INT32_MAX, "nnet_forward: too many tiles");
     p.num_tiles = static_cast<int>(tiles);
     p.num_kb = st.k_pad / kBlockK;
+    p.num_kb8 = st.c8 ? st.k_pad8 / 128 : 0;
+    p.acc_scale = st.c8 ? ldexpf(1.0f, -st.w_exp) : 1.0f;
     p.N_valid = st.out_dim;
     p.bias = st.bias.as<float>();
     p.in_sumsq = in_sumsq;
@@ -356,14 +439,16 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
     if (!final) {
       const int buf = static_cast<int>(i & 1);
       p.out_hi = ws->act_hi[buf].as<__nv_bfloat16>();
-      p.out_lo = am->planes == 2 ? ws->act_lo[buf].as<__nv_bfloat16>() : nullptr;
+      p.out_lo = (am->planes == 2 && !am->c8) ? ws->act_lo[buf].as<__nv_bfloat16>() : nullptr;
+      p.out8_lo = out8 ? ws->act8_lo[buf].as<uint8_t>() : nullptr;
+      p.out8_hi = out8 ? ws->act8_hi[buf].as<uint8_t>() : nullptr;
       p.ld_out = st.n_pad;
       p.out_sumsq = st.normalize ? ws->sumsq[buf].as<float>() : nullptr;
     } else {
       p.out_f32 = d_out;
       p.ld_f32 = st.out_dim;
       // softmax + AM epilogue are fused into this GEMM (no second pass over the output)
-      p.final_mode = am->softmax_last ? (mode == kFinalCompact ? 3 : (mode == kFinalLoglik ? 2 : (mode == kFinalProb ? 1 : 0))) : 0;
+      p.final_mode = am->softmax_last ? (mode_out == kFinalCompact ? 3 : (mode_out == kFinalLoglik ? 2 : (mode_out == kFinalProb ? 1 : 0))) : 0;
       if (p.final_mode == 3) {
         PKB_REQUIRE(d_h16 && d_off, "nnet_forward: the compact output needs its two buffers");
         p.out_h16 = d_h16;
@@ -377,25 +462,37 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       p.log_floor = static_cast<float>(log(static_cast<double>(static_cast<float>(1.0e-20))));
     }
     // CTA pairs (cta_group::2) whenever the tile is 256 wide and there is at least one full pair
-    // of row blocks: always for hidden stages; for the output stage only in BF16X3, where the
-    // halved W tile is what makes a second pipeline stage fit (its BF16/FP16 variant is bound by
-    // the epilogue, not by operand traffic, and measured no gain from pairing)
+    // of row blocks: always for hidden stages; for the output stage only in the multi-MMA modes,
+    // where the halved W tile is what makes a second pipeline stage fit (its BF16/FP16 variant is
+    // bound by the epilogue, not by operand traffic, and measured no gain from pairing)
     static const bool no_pairs = getenv("PKB_GEMM_CG1") != nullptr;
     static const bool final_pairs = getenv("PKB_GEMM_FINAL_CG2") != nullptr;
-    const bool want_pair = !final || am->planes == 2 || final_pairs;
+    const bool want_pair = !final || mode >= 2 || final_pairs;
     int cg = (want_pair && st.block_n == 256 && m_tiles >= 2 && !no_pairs) ? 2 : 1;
     // the grouped schedule of the softmax stage needs one CTA (pair) per column tile on the device
     if (final && p.final_mode != 0 && cg == 2 && (c->sm_count / 2) / p.n_tiles_n < 1) cg = 1;
-    PKB_TRY(launch_gemm(c, st.block_n, am->planes, final, cg, &tm_a_hi, &tm_a_lo,
-                        cg == 2 ? &st.tm_w_hi_half : &st.tm_w_hi,
-                        cg == 2 ? &st.tm_w_lo_half : &st.tm_w_lo, p));
+    GemmMaps maps;
+    maps.a_hi = &tm_a_hi;
+    maps.a_lo = &tm_a_lo;
+    maps.a_x = &tm_a_x;
+    maps.w_hi = cg == 2 ? &st.tm_w_hi_half : &st.tm_w_hi;
+    if (mode == 3) {
+      maps.w_lo = cg == 2 ? &st.tm_w8_lo_half : &st.tm_w8_lo;
+      maps.w_x = cg == 2 ? &st.tm_w8_hi_half : &st.tm_w8_hi;
+    } else {
+      maps.w_lo = cg == 2 ? &st.tm_w_lo_half : &st.tm_w_lo;
+      maps.w_x = maps.w_hi;
+    }
+    PKB_TRY(launch_gemm(c, st.block_n, mode, final, cg, out8, maps, p));
     if (!final) {
       a_hi = p.out_hi;
       a_lo = p.out_lo;
+      a8_lo = p.out8_lo;
+      a8_hi = p.out8_hi;
       a_cols = st.n_pad;
       a_pitch = st.n_pad;
       in_sumsq = p.out_sumsq;
-      in_sumsq_tiles = p.n_tiles_n * sumsq_parts(am->planes);
+      in_sumsq_tiles = p.n_tiles_n * sumsq_parts(mode);
       in_dim = static_cast<float>(st.out_dim);
     }
   }

@@ -19,6 +19,12 @@ struct Stage {
   DevBuf w_hi, w_lo, bias;      // [n_pad][k_pad] BF16 planes, [n_pad] FP32
   CUtensorMap tm_w_hi, tm_w_lo;
   CUtensorMap tm_w_hi_half, tm_w_lo_half;  // box rows block_n / 2: W halves of a CTA pair
+  // operand mode 3 (FP16C8): w_hi holds fp16(W * 2^w_exp); E4M3 planes [n_pad][k_pad8]
+  bool c8 = false;
+  int w_exp = 0;                // g: stored weights are W * 2^g with max |W * 2^g| in [1, 2)
+  int k_pad8 = 0;               // K padded to 128
+  DevBuf w8_hi, w8_lo;          // e4m3(W16 * 2^4), e4m3((W * 2^g - W16) * 2^13)
+  CUtensorMap tm_w8_hi, tm_w8_lo, tm_w8_hi_half, tm_w8_lo_half;
 };
 
 // How the final stage's logits are turned into the caller's output.
@@ -42,6 +48,7 @@ struct InputView {
 struct Workspace {
   int64_t rows = 0;  // M of every GEMM
   DevBuf act_hi[2], act_lo[2], sumsq[2], lse_part, mzl_part, tile_done, row_map;
+  DevBuf act8_lo[2], act8_hi[2];  // FP16C8: E4M3 correction operands of the hidden activations
   // padded feature planes of the batch pipeline
   DevBuf feat_hi, feat_lo, pad_off;
   void release();
@@ -52,8 +59,9 @@ struct Workspace {
 struct pkb_am {
   pkb::Ctx *c = nullptr;
   int precision = PKB_PREC_BF16;
-  int planes = 1;
-  int fp16 = 0;  // operands are FP16 instead of BF16 (PKB_PREC_FP16)
+  int planes = 1;  // 16-bit planes of the input features and of stage 0
+  int fp16 = 0;    // operands are FP16 instead of BF16 (PKB_PREC_FP16, _FP16X3, _FP16C8)
+  int c8 = 0;      // PKB_PREC_FP16C8: stages after the first run in operand mode 3
   int left = 0, right = 0, num_pdfs = 0;
   int input_dim = 0;   // nnet input dim
   int feat_dim = 0;    // input_dim / (left + right + 1) when divisible, else 0

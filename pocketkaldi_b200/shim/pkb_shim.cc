@@ -27,11 +27,14 @@ pkb_ctx_t *shim_ctx() {
   return ctx;
 }
 
-// GEMM arithmetic from PKB_PRECISION: "bf16", "fp16" or "bf16x3" (default: the parity mode).
+// GEMM arithmetic from PKB_PRECISION: "bf16", "fp16", "bf16x3", "fp16x3" or "fp16c8" (default:
+// bf16x3, a mode that meets the parity bar).
 int shim_precision() {
   const char *p = getenv("PKB_PRECISION");
   if (p != nullptr && strcmp(p, "bf16") == 0) return PKB_PREC_BF16;
   if (p != nullptr && strcmp(p, "fp16") == 0) return PKB_PREC_FP16;
+  if (p != nullptr && strcmp(p, "fp16x3") == 0) return PKB_PREC_FP16X3;
+  if (p != nullptr && strcmp(p, "fp16c8") == 0) return PKB_PREC_FP16C8;
   return PKB_PREC_BF16X3;
 }
 

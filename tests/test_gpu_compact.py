@@ -67,8 +67,8 @@ def test_compact_matches_fp32_output(ctx, pdfs, hidden, prior_kind):
     top = full.argmax(1)
     assert np.array_equal(exp.argmax(1), top)
     assert np.max(err[np.arange(len(top)), top]) <= 1e-6
-    # every stored value is <= 0 (the offset is the frame's maximum)
-    assert np.all(h.view(np.float16) <= 0)
+    # every stored value is <= 0 up to FP32 rounding of the two subtraction orders (the offset is the frame maximum)
+    assert np.all(h.view(np.float16) <= 1e-4)
 
 
 def test_compact_vs_oracle_and_floor(ctx, oracle):
@@ -91,7 +91,8 @@ def test_compact_vs_oracle_and_floor(ctx, oracle):
     b.close()
     am.close()
     ref = oracle.am_compute(feats, layers, prior, 5, 5)
-    assert (ref <= np.log(1e-20) + 2.0).mean() > 0.2      # the floor really binds in this fixture
+    floored = ref + np.log(prior)[None, :] <= np.log(1e-20) + 1e-3
+    assert floored.mean() > 0.2                           # the floor really binds in this fixture
     d = np.abs(exp - ref)
     near = ref >= ref.max(1, keepdims=True) - 30.0
     assert d[near].max() <= LL_TOL

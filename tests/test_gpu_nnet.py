@@ -61,6 +61,8 @@ def test_gemm_differential(ctx, oracle, m, n, k):
     assert np.max(np.abs(y3 - ref) / np.maximum(1.0, np.abs(ref))) < 2e-5
     y1 = pk.Nnet(ctx, pk.PREC_BF16).from_layers([("linear", W, b)]).Propagate(A)
     assert np.max(np.abs(y1 - ref) / np.maximum(1.0, np.abs(ref))) < 1e-2
+    yh = pk.Nnet(ctx, pk.PREC_FP16X3).from_layers([("linear", W, b)]).Propagate(A)
+    assert np.max(np.abs(yh - ref) / np.maximum(1.0, np.abs(ref))) < 2e-6 * max(1.0, k ** 0.5)
     if m * n * k <= 512 ** 3:
         yo = oracle.linear(A, W, b)
         assert np.max(np.abs(y3 - yo) / np.maximum(1.0, np.abs(yo))) < 2e-5
@@ -119,6 +121,58 @@ def test_mid_size_dnn_vs_oracle(ctx, oracle, normalize):
     for o, r in zip(am1.compute_batch(feats), ref):
         assert np.max(np.abs(o - r)) < 0.5
         assert np.mean(o.argmax(1) == r.argmax(1)) >= 0.9
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("prec", ["PREC_FP16C8", "PREC_FP16X3"])
+def test_fp8_corrected_and_split_fp16_modes_vs_oracle(ctx, oracle, prec, normalize):
+    # FP16C8 (FP16 product + FP8 first-order corrections, operand mode 3 from the second layer on)
+    # and FP16X3 on a 4-layer net with odd widths: hidden 320 (block_n 128 + K tail of the FP8
+    # k-blocks), 512 (block_n 256, CTA pairs), 1000 pdfs; ragged batch
+    rng = np.random.default_rng(23)
+    layers = []
+    d = 440
+    for o in (320, 512, 256):
+        layers += [("linear", (rng.standard_normal((o, d)) * np.sqrt(2.0 / d)).astype(np.float32),
+                    (rng.standard_normal(o) * 0.1).astype(np.float32)), ("relu",)]
+        if normalize:
+            layers.append(("normalize",))
+        d = o
+    layers += [("linear", (rng.standard_normal((1000, d)) * np.sqrt(2.0 / d)).astype(np.float32),
+                (rng.standard_normal(1000) * 0.1).astype(np.float32)), ("softmax",)]
+    prior = rng.uniform(0.5, 1.5, 1000).astype(np.float32)
+    prior /= prior.sum()
+    feats = [(rng.standard_normal((n, 40)) * 2.5).astype(np.float32) for n in (300, 1, 420)]
+    ref = [oracle.am_compute(f, layers, prior, 5, 5) for f in feats]
+    am = pk.AcousticModel(ctx, getattr(pk, prec)).from_layers(layers, prior, 5, 5)
+    worst = 0.0
+    for o, r in zip(am.compute_batch(feats), ref):
+        worst = max(worst, float(np.max(np.abs(o - r))))
+        assert np.mean(o.argmax(1) == r.argmax(1)) >= ARGMAX_MIN
+    am.close()
+    print(prec, "max |dLL|", worst)
+    # both are far inside the 2e-2 bar: ~2^-15 relative for FP16C8, FP32-class for FP16X3
+    assert worst < (2e-3 if prec == "PREC_FP16C8" else 2e-4)
+
+
+def test_fp16c8_linear_layers_alone(ctx):
+    # operand mode 3 in isolation: two linear layers (the second one runs FP16 + FP8 corrections)
+    # against float64, with weights and activations of very different magnitudes per layer
+    rng = np.random.default_rng(3)
+    for scale_w, scale_a, k, n in ((0.03, 1.0, 1024, 512), (4.0, 0.02, 200, 130), (1e-3, 30.0, 640, 1024)):
+        W1 = np.eye(k, dtype=np.float32)
+        b1 = np.zeros(k, np.float32)
+        W2 = (rng.standard_normal((n, k)) * scale_w).astype(np.float32)
+        b2 = rng.standard_normal(n).astype(np.float32)
+        A = np.abs(rng.standard_normal((257, k)) * scale_a).astype(np.float32)
+        ref = A.astype(np.float64) @ W2.astype(np.float64).T + b2
+        y8 = pk.Nnet(ctx, pk.PREC_FP16C8).from_layers([("linear", W1, b1), ("linear", W2, b2)]).Propagate(A)
+        y1 = pk.Nnet(ctx, pk.PREC_FP16).from_layers([("linear", W1, b1), ("linear", W2, b2)]).Propagate(A)
+        norm = np.sqrt((A.astype(np.float64) ** 2) @ (W2.astype(np.float64).T ** 2))  # sqrt(sum (a w)^2)
+        e8 = float(np.max(np.abs(y8 - ref) / norm))
+        e1 = float(np.max(np.abs(y1 - ref) / norm))
+        print("k=%d n=%d: fp16c8 %.2e, fp16 %.2e (relative to the product norm)" % (k, n, e8, e1))
+        assert e8 < 1.5e-4 and e8 < e1 / 4
 
 
 def test_fused_pcm_to_loglik(ctx, golden, toy_conf):

@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 METRIC = "acoustic frames/s (fbank+CMVN+nnet loglik)"
 # The precision the headline is quoted in. tests/test_gpu_baseline_nets.py asserts the
 # north_star parity bar for this mode on the config-3 and config-4 nets.
-DEFAULT_PRECISION = "bf16x3"
+DEFAULT_PRECISION = "fp16c8"
 LL_TOL, ARGMAX_MIN, FEAT_TOL = 2e-2, 0.999, 1e-4
 SAMPLES_10S = 160000
 FRAMES_10S = 998
@@ -399,8 +399,7 @@ def run_gpu_arm(args, cfg):
     if rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         try:
-            n_par = 3 if cfg["width"] <= 1024 else 1
-            ref_pack = reference_outputs(cfg, env.g, n_par)
+            ref_pack = reference_outputs(cfg, env.g, 3)
             batch.run(pk.STAGE_ALL)  # once with the FP32 feature copy for the comparison
             parity = parity_sample(cfg, batch, ref_pack)
             if world == 1:
@@ -468,7 +467,7 @@ def sub_config(env, key, precision, with_parity, n_utts=None):
     res.pop("clocks")
     if with_parity:
         try:
-            ref_pack = reference_outputs(cfg, env.g, 1)
+            ref_pack = reference_outputs(cfg, env.g, 3 if cfg["nnet"] else 1)
             batch.run(pk.STAGE_ALL)
             res["parity"] = parity_sample(cfg, batch, ref_pack)
             res["parity_ok"] = parity_ok(res["parity"], cfg["nnet"])

@@ -93,6 +93,18 @@ int pkb_fbank_f32(pkb_ctx_t *ctx, const float *wave, const int32_t *num_samples,
 int pkb_fbank_i16(pkb_ctx_t *ctx, const int16_t *pcm, const int32_t *num_samples,
                   int n_utts, float *feats_out, int32_t *num_frames_out);
 
+/* Front-end options that BASELINE.json's north_star names but the reference does not have
+ * (its Fbank is fixed: no dither, Hamming window -- src/fbank.cc:44-100,249-256). Both default to
+ * the reference's behaviour and are PARITY UNPINNED: no reference output exists for them; they
+ * follow Kaldi's definitions and are covered by property tests only.
+ *   window_type  PKB_WINDOW_HAMMING, or PKB_WINDOW_POVEY = pow(0.5 - 0.5 cos(2 pi i / 399), 0.85)
+ *   dither       every sample of every frame window gets dither * N(0,1) added before DC removal
+ *                (Kaldi's --dither); the noise is a counter-based stream keyed by (dither_seed,
+ *                utterance index in the call, frame, sample), so runs are reproducible. 0 = off. */
+#define PKB_WINDOW_HAMMING 0
+#define PKB_WINDOW_POVEY 1
+int pkb_fbank_set_options(pkb_ctx_t *ctx, int window_type, float dither, uint64_t dither_seed);
+
 /* ---- CMVN (CMVN::CMVN + GetFrame for t = 0..T-1, src/cmvn.cc:103-125) -----*/
 /* raw / out: [sum_u T_u][40]; global_stats: 40 sums + count
  * (the "cmvn_stats" VEC0 of pk_load, src/pocketkaldi.cc:96-104). The float
@@ -107,8 +119,14 @@ int pkb_cmvn(pkb_ctx_t *ctx, const float *raw, const int32_t *num_frames, int n_
  * readers of src/nnet.cc:80-147, src/matrix.cc:287-319, src/vector.cc:392-425. */
 int pkb_am_load(pkb_ctx_t *ctx, const char *conf_path, int precision, pkb_am_t **am);
 
+/* A layer type the reference does not have (its set is {Linear, ReLU, Normalize, Softmax},
+ * src/nnet.h:28-33; 4 and 5 are the converter's ADD / MUL): logistic sigmoid, accepted where a
+ * ReLU is. BASELINE.json's north_star names it; PARITY UNPINNED (no reference output exists),
+ * checked against a float64 evaluation only. The file loader accepts it as LAY0 type 6. */
+#define PKB_LAYER_SIGMOID 6
+
 /* Same model from memory. layer_types[i] in {0 linear, 1 relu, 2 normalize,
- * 3 softmax} (src/nnet.h:28-33); for linear layer number j (in order)
+ * 3 softmax} (src/nnet.h:28-33) or PKB_LAYER_SIGMOID; for linear layer number j (in order)
  * weights[j] is W[out][in] row-major as on disk, biases[j] is b[out],
  * out_dims[j] / in_dims[j] its shape. prior holds probabilities (log is taken
  * here, as src/am.cc:42-43 does). tid2pdf may be NULL. */

@@ -58,6 +58,7 @@ _SIGNATURES = [
     ("pkb_device_sm_count", C.c_int, [_VP]),
     ("pkb_device_name", C.c_char_p, [_VP]),
     ("pkb_fbank_num_frames", C.c_int, [C.c_int]),
+    ("pkb_fbank_set_options", C.c_int, [_VP, C.c_int, C.c_float, C.c_uint64]),
     ("pkb_fbank_f32", C.c_int, [_VP, _f32p, _i32p, C.c_int, _f32p, _i32p]),
     ("pkb_fbank_i16", C.c_int, [_VP, _i16p, _i32p, C.c_int, _f32p, _i32p]),
     ("pkb_cmvn", C.c_int, [_VP, _f32p, _i32p, C.c_int, _f32p, _f32p]),
@@ -291,6 +292,11 @@ class Context:
         _check(self.lib.pkb_profile_get(self.h, launches, ms))
         return {k: (int(launches[i]), float(ms[i])) for i, k in enumerate(KERNEL_CLASSES)}
 
+    def set_fbank_options(self, window="hamming", dither=0.0, dither_seed=0):
+        """Front-end options the reference does not have (pkb_fbank_set_options): parity unpinned."""
+        _check(self.lib.pkb_fbank_set_options(self.h, {"hamming": 0, "povey": 1}[window], dither,
+                                              dither_seed))
+
     def flush_l2(self):
         _check(self.lib.pkb_flush_l2(self.h))
 
@@ -379,7 +385,7 @@ class AcousticModel:
         if any(l[0] == "mul" for l in layers):
             from .formats import fold_mul_layers
             layers = fold_mul_layers(layers)
-        names = {"linear": 0, "relu": 1, "normalize": 2, "softmax": 3}
+        names = {"linear": 0, "relu": 1, "normalize": 2, "softmax": 3, "sigmoid": 6}
         types = np.array([names[l[0]] for l in layers], np.int32)
         Ws = [_f32(l[1]) for l in layers if l[0] == "linear"]
         bs = [_f32(l[2]) for l in layers if l[0] == "linear"]

@@ -182,7 +182,7 @@ int read_nnet(const std::string &path, HostNnet *net) {
         for (size_t j = 0; j < v.size(); ++j) pending_scale[j] *= v[j];
       }
       continue;  // not a layer of the executed stack
-    } else if (type < 0 || type > 3) {
+    } else if ((type < 0 || type > 3) && type != PKB_LAYER_SIGMOID) {
       // ADD (4) is defined by the converter but never written by it; rejected like the
       // reference reader does (src/nnet.cc:122-126)
       pkb::set_error("Corruption: read_layer: unexpected layer type: %d (%s)", type, path.c_str());

@@ -26,13 +26,14 @@ namespace {
 
 constexpr int kCmvnUnroll = 8;
 
-// Where one chain reads and writes. Everything is indexed by frame with a stride of one frame.
+// Where one thread's pair of chains (dims d, d + 1 of one utterance) reads and writes. Everything
+// is indexed by frame with a stride of one frame.
 struct CmvnChain {
-  const float *x;         // raw[t * 40]
-  float *y;               // out[t * 40] or nullptr
-  __nv_bfloat16 *ph, *pl; // planes[(left + t) * dim_pad] or nullptr
+  const float *x;         // raw[t * 40 + d]
+  float *y;               // out[t * 40 + d] or nullptr
+  __nv_bfloat16 *ph, *pl; // planes[(left + t) * dim_pad + d] or nullptr
   int dim_pad;
-  float gd;               // global stat of this dim
+  float gd[2];            // global stats of the two dims
 };
 
 // RN32(a + b + c) for binary32 a, b, c without widening: Boldo & Melquiond's three-term sum
@@ -62,43 +63,59 @@ __device__ __forceinline__ bool cmvn_out_of_range(float x) {
   return u != 0u && (u - 0x3C800000u) >= (0x45800000u - 0x3C800000u);
 }
 
-// One frame of the recurrence (ComputeStats -> SmoothStats -> Apply, src/cmvn.cc:35-101).
+// One frame of the recurrence (ComputeStats -> SmoothStats -> Apply, src/cmvn.cc:35-101) for the
+// thread's two independent chains (the compiler interleaves them: twice the work per dependent
+// step of latency).
 //   kSub:   the window is full, the frame 600 steps back leaves the sum (t >= 600)
 //   kAlpha: fewer than 600 frames seen, the global stats are blended in (t < 599)
 //   kF64:   widen like the reference (only needed for kSub, see above)
 template <bool kSub, bool kAlpha, bool kF64, int kPlanes, bool kFp16, bool kOut>
-__device__ __forceinline__ void cmvn_frame(const CmvnChain &c, int t, int i, float x, float xold, float &stat,
-                                           float alpha, float sc) {
+__device__ __forceinline__ void cmvn_frame(const CmvnChain &c, int t, int i, float2 x, float2 xold,
+                                           float (&stat)[2], float alpha, float sc) {
   // t = first frame of the group, i = compile-time index inside it: every address below is one
   // group base plus an immediate offset
-  if (!kSub) {
-    // double(stat) + double(x) rounded to float == the float sum: the double sum is exact when
-    // the exponents are within 29 of each other and cannot reach a rounding boundary otherwise
-    stat = __fadd_rn(stat, x);
-  } else if (kF64) {
-    double acc = static_cast<double>(stat) + static_cast<double>(x);
-    acc += -1.0 * static_cast<double>(xold);
-    stat = static_cast<float>(acc);
-  } else {
-    stat = sum3_rn(stat, x, -xold);
+  const float xv[2] = {x.x, x.y}, xo[2] = {xold.x, xold.y};
+  float v[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (!kSub) {
+      // double(stat) + double(x) rounded to float == the float sum: the double sum is exact when
+      // the exponents are within 29 of each other and cannot reach a rounding boundary otherwise
+      stat[e] = __fadd_rn(stat[e], xv[e]);
+    } else if (kF64) {
+      double acc = static_cast<double>(stat[e]) + static_cast<double>(xv[e]);
+      acc += -1.0 * static_cast<double>(xo[e]);
+      stat[e] = static_cast<float>(acc);
+    } else {
+      stat[e] = sum3_rn(stat[e], xv[e], -xo[e]);
+    }
+    float s = stat[e];
+    if (kAlpha) s = __fadd_rn(s, __fmul_rn(alpha, c.gd[e]));
+    v[e] = __fadd_rn(xv[e], __fmul_rn(-sc, s));
   }
-  float s = stat;
-  if (kAlpha) s = __fadd_rn(s, __fmul_rn(alpha, c.gd));
-  const float v = __fadd_rn(x, __fmul_rn(-sc, s));
-  if (kOut) (c.y + static_cast<int64_t>(t) * kMel)[i * kMel] = v;
+  // streaming stores: the outputs are not read again by this kernel and must not evict the
+  // raw rows that are (x[t - 600])
+  if (kOut) __stcs(reinterpret_cast<float2 *>(c.y + static_cast<int64_t>(t) * kMel + i * kMel), make_float2(v[0], v[1]));
   if (kPlanes >= 1) {
     // plane rows are kMel elements apart (feat_dim_pad == kMel: 40 is a multiple of 8)
-    const __nv_bfloat16 h = operand_bits(v, kFp16);
-    (c.ph + static_cast<int64_t>(t) * kMel)[i * kMel] = h;
-    if (kPlanes == 2)
-      (c.pl + static_cast<int64_t>(t) * kMel)[i * kMel] = operand_bits(v - operand_value(h, kFp16), kFp16);
+    const __nv_bfloat16 h0 = operand_bits(v[0], kFp16), h1 = operand_bits(v[1], kFp16);
+    __stcs(reinterpret_cast<unsigned int *>(c.ph + static_cast<int64_t>(t) * kMel + i * kMel),
+           static_cast<unsigned int>(__bfloat16_as_ushort(h0)) |
+               (static_cast<unsigned int>(__bfloat16_as_ushort(h1)) << 16));
+    if (kPlanes == 2) {
+      const __nv_bfloat16 l0 = operand_bits(v[0] - operand_value(h0, kFp16), kFp16);
+      const __nv_bfloat16 l1 = operand_bits(v[1] - operand_value(h1, kFp16), kFp16);
+      __stcs(reinterpret_cast<unsigned int *>(c.pl + static_cast<int64_t>(t) * kMel + i * kMel),
+             static_cast<unsigned int>(__bfloat16_as_ushort(l0)) |
+                 (static_cast<unsigned int>(__bfloat16_as_ushort(l1)) << 16));
+    }
   }
 }
 
-// cp.async: 4 bytes global -> shared without passing through a register; completion is tracked
+// cp.async: 8 bytes global -> shared without passing through a register; completion is tracked
 // per thread in commit groups.
-__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+__device__ __forceinline__ void cp_async8(float2 *smem_dst, const float *gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(
                    static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
                "l"(gmem_src)
                : "memory");
@@ -109,19 +126,19 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
-constexpr int kCmvnGroups = 4;                       // groups of kCmvnUnroll frames in flight per chain
-constexpr int kCmvnRing = kCmvnGroups * kCmvnUnroll;  // 32 frames
 
-// One thread per chain (utterance, dim). The recurrence is a handful of dependent FP32
-// operations per frame, so what limits the kernel is how many bytes each chain keeps in flight:
-// every thread streams its x[t] and x[t - 600] through a private shared-memory ring with
-// cp.async, three groups (24 frames) ahead of the group it is consuming, and no thread ever
-// reads another thread's slots (no block-level synchronisation in the loop).
+// One thread per pair of chains (utterance, dims 2k and 2k + 1): 20 threads per utterance. The
+// recurrence is a handful of dependent FP32 operations per frame, so what limits the kernel is
+// latency: every thread streams its x[t] and x[t - 600] pairs through a private shared-memory ring
+// with cp.async, kGroups - 1 groups of 8 frames ahead of the group it is consuming, and no thread
+// ever reads another thread's slots (no block-level synchronisation in the loop).
 // Frames t < 600 fill the window (global stats blended in through the alpha / scale tables, which
 // hold alpha = 0 at t = 599); frames t >= 600 slide it. 600 is a multiple of the group size, so a
 // group lies in one phase.
-template <int kPlanes, bool kFp16, bool kOut, int kBlock>
-__global__ void __launch_bounds__(kBlock, kBlock == 160 ? 5 : 16)
+constexpr int kCmvnThreadsPerUtt = kMel / 2;
+
+template <int kPlanes, bool kFp16, bool kOut, int kBlock, int kCmvnGroups>
+__global__ void __launch_bounds__(kBlock, kBlock == 160 ? 2 : 16)
 cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off,
             const int32_t *__restrict__ num_frames, int n_utts,
             const float *__restrict__ tab /* alpha[600], scale[600], global[41] */,
@@ -129,72 +146,76 @@ cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off
             __nv_bfloat16 *__restrict__ p_lo, const int64_t *__restrict__ pad_off, int left,
             int right, int dim_pad) {
   static_assert(kCmvnWindow % kCmvnUnroll == 0, "a group must not straddle the two phases");
+  static_assert(kMel % 2 == 0, "two dims per thread");
+  constexpr int kCmvnRing = kCmvnGroups * kCmvnUnroll;  // frames in flight per chain (power of two)
   __shared__ float s_alpha[kCmvnWindow];
   __shared__ float s_scale[kCmvnWindow];
-  extern __shared__ float s_ring[];  // [2][kCmvnRing][kBlock]: x, then x_old
+  extern __shared__ float2 s_ring[];  // [2][kCmvnRing][kBlock]: x, then x_old
   for (int i = threadIdx.x; i < kCmvnWindow; i += kBlock) {
     s_alpha[i] = tab[i];
     s_scale[i] = tab[kCmvnWindow + i];
   }
   __syncthreads();
   const int64_t g = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
-  const int u = static_cast<int>(g / kMel);
-  const int d = static_cast<int>(g % kMel);
+  const int u = static_cast<int>(g / kCmvnThreadsPerUtt);
+  const int d = 2 * static_cast<int>(g % kCmvnThreadsPerUtt);
   if (u >= n_utts) return;
   const int T = num_frames[u];
   if (T == 0) return;
   CmvnChain c;
-  c.gd = tab[2 * kCmvnWindow + d];
+  c.gd[0] = tab[2 * kCmvnWindow + d];
+  c.gd[1] = tab[2 * kCmvnWindow + d + 1];
   c.x = raw + frame_off[u] * kMel + d;
   c.y = kOut ? out + frame_off[u] * kMel + d : nullptr;
   c.dim_pad = dim_pad;
   c.ph = kPlanes >= 1 ? p_hi + (pad_off[u] + left) * dim_pad + d : nullptr;
   c.pl = kPlanes == 2 ? p_lo + (pad_off[u] + left) * dim_pad + d : nullptr;
 
-  float *rx = s_ring + threadIdx.x;
-  float *ro = rx + kCmvnRing * kBlock;
+  float2 *rx = s_ring + threadIdx.x;
+  float2 *ro = rx + kCmvnRing * kBlock;
   const int T8 = T & ~(kCmvnUnroll - 1);  // whole groups run without per-frame bounds checks
   // one commit group per call (possibly empty) keeps the wait count static
   auto issue = [&](int t0) {
     if (t0 < T8) {
       const float *px = c.x + static_cast<int64_t>(t0) * kMel;
-      float *dx = rx + (t0 & (kCmvnRing - 1)) * kBlock;
+      float2 *dx = rx + (t0 & (kCmvnRing - 1)) * kBlock;
 #pragma unroll
-      for (int i = 0; i < kCmvnUnroll; ++i) cp_async4(dx + i * kBlock, px + i * kMel);
+      for (int i = 0; i < kCmvnUnroll; ++i) cp_async8(dx + i * kBlock, px + i * kMel);
       if (t0 >= kCmvnWindow) {
-        float *dxo = ro + (t0 & (kCmvnRing - 1)) * kBlock;
+        float2 *dxo = ro + (t0 & (kCmvnRing - 1)) * kBlock;
 #pragma unroll
-        for (int i = 0; i < kCmvnUnroll; ++i) cp_async4(dxo + i * kBlock, px + (i - kCmvnWindow) * kMel);
+        for (int i = 0; i < kCmvnUnroll; ++i) cp_async8(dxo + i * kBlock, px + (i - kCmvnWindow) * kMel);
       }
     }
     cp_async_commit();
   };
 
-  float stat = 0.0f;
+  float stat[2] = {0.0f, 0.0f};
   bool wide = false;
   const float scale_full = s_scale[kCmvnWindow - 1];
+  const float2 zero2 = make_float2(0.0f, 0.0f);
 #pragma unroll
   for (int k = 0; k < kCmvnGroups - 1; ++k) issue(k * kCmvnUnroll);
   for (int t0 = 0; t0 < T8; t0 += kCmvnUnroll) {
     issue(t0 + (kCmvnGroups - 1) * kCmvnUnroll);
     cp_async_wait<kCmvnGroups - 1>();  // the group of t0 has landed
-    const float *gx = rx + (t0 & (kCmvnRing - 1)) * kBlock;
-    float xv[kCmvnUnroll];
+    const float2 *gx = rx + (t0 & (kCmvnRing - 1)) * kBlock;
+    float2 xv[kCmvnUnroll];
     bool w = wide;
 #pragma unroll
     for (int i = 0; i < kCmvnUnroll; ++i) {
       xv[i] = gx[i * kBlock];
-      w = w || cmvn_out_of_range(xv[i]);
+      w = w || cmvn_out_of_range(xv[i].x) || cmvn_out_of_range(xv[i].y);
     }
     wide = w;
     if (t0 < kCmvnWindow) {
       const float *pa = s_alpha + t0, *ps = s_scale + t0;
 #pragma unroll
       for (int i = 0; i < kCmvnUnroll; ++i)
-        cmvn_frame<false, true, false, kPlanes, kFp16, kOut>(c, t0, i, xv[i], 0.0f, stat, pa[i], ps[i]);
+        cmvn_frame<false, true, false, kPlanes, kFp16, kOut>(c, t0, i, xv[i], zero2, stat, pa[i], ps[i]);
     } else {
-      const float *go = ro + (t0 & (kCmvnRing - 1)) * kBlock;
-      float xp[kCmvnUnroll];
+      const float2 *go = ro + (t0 & (kCmvnRing - 1)) * kBlock;
+      float2 xp[kCmvnUnroll];
 #pragma unroll
       for (int i = 0; i < kCmvnUnroll; ++i) xp[i] = go[i * kBlock];
       if (w) {
@@ -210,12 +231,12 @@ cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off
   }
   // the last T % 8 frames, one at a time straight from global memory
   for (int t = T8; t < T; ++t) {
-    const float x = c.x[static_cast<int64_t>(t) * kMel];
-    wide = wide || cmvn_out_of_range(x);
+    const float2 x = *reinterpret_cast<const float2 *>(c.x + static_cast<int64_t>(t) * kMel);
+    wide = wide || cmvn_out_of_range(x.x) || cmvn_out_of_range(x.y);
     if (t < kCmvnWindow) {
-      cmvn_frame<false, true, false, kPlanes, kFp16, kOut>(c, t, 0, x, 0.0f, stat, s_alpha[t], s_scale[t]);
+      cmvn_frame<false, true, false, kPlanes, kFp16, kOut>(c, t, 0, x, zero2, stat, s_alpha[t], s_scale[t]);
     } else {
-      const float xo = c.x[static_cast<int64_t>(t - kCmvnWindow) * kMel];
+      const float2 xo = *reinterpret_cast<const float2 *>(c.x + static_cast<int64_t>(t - kCmvnWindow) * kMel);
       if (wide) cmvn_frame<true, false, true, kPlanes, kFp16, kOut>(c, t, 0, x, xo, stat, 0.0f, scale_full);
       else cmvn_frame<true, false, false, kPlanes, kFp16, kOut>(c, t, 0, x, xo, stat, 0.0f, scale_full);
     }
@@ -224,13 +245,16 @@ cmvn_kernel(const float *__restrict__ raw, const int64_t *__restrict__ frame_off
   // replicated edge rows of the padded planes (AcousticModel::SpliceFeats clamps at the
   // utterance edges, src/am.cc:65-88): copies of this thread's own first / last element
   if (kPlanes >= 1) {
-    const __nv_bfloat16 h0 = c.ph[0], h1 = c.ph[static_cast<int64_t>(T - 1) * dim_pad];
-    for (int r = 1; r <= left; ++r) c.ph[-static_cast<int64_t>(r) * dim_pad] = h0;
-    for (int r = 0; r < right; ++r) c.ph[static_cast<int64_t>(T + r) * dim_pad] = h1;
+    typedef unsigned int u32;
+    const u32 h0 = *reinterpret_cast<const u32 *>(c.ph);
+    const u32 h1 = *reinterpret_cast<const u32 *>(c.ph + static_cast<int64_t>(T - 1) * dim_pad);
+    for (int r = 1; r <= left; ++r) *reinterpret_cast<u32 *>(c.ph - static_cast<int64_t>(r) * dim_pad) = h0;
+    for (int r = 0; r < right; ++r) *reinterpret_cast<u32 *>(c.ph + static_cast<int64_t>(T + r) * dim_pad) = h1;
     if (kPlanes == 2) {
-      const __nv_bfloat16 l0 = c.pl[0], l1 = c.pl[static_cast<int64_t>(T - 1) * dim_pad];
-      for (int r = 1; r <= left; ++r) c.pl[-static_cast<int64_t>(r) * dim_pad] = l0;
-      for (int r = 0; r < right; ++r) c.pl[static_cast<int64_t>(T + r) * dim_pad] = l1;
+      const u32 l0 = *reinterpret_cast<const u32 *>(c.pl);
+      const u32 l1 = *reinterpret_cast<const u32 *>(c.pl + static_cast<int64_t>(T - 1) * dim_pad);
+      for (int r = 1; r <= left; ++r) *reinterpret_cast<u32 *>(c.pl - static_cast<int64_t>(r) * dim_pad) = l0;
+      for (int r = 0; r < right; ++r) *reinterpret_cast<u32 *>(c.pl + static_cast<int64_t>(T + r) * dim_pad) = l1;
     }
   }
 }
@@ -317,13 +341,16 @@ int launch_cmvn(Ctx *c, const float *d_raw, const BatchMeta &m, float *d_out,
                 const PaddedPlanes *planes) {
   if (m.n_utts == 0 || m.total_frames == 0) return PKB_OK;
   PKB_REQUIRE(c->cmvn_valid, "cmvn: tables not prepared");
-  const int64_t threads = static_cast<int64_t>(m.n_utts) * kMel;
-  // a chain is sequential in t, so parallelism is n_utts * 40 threads: small batches run as
+  const int64_t threads = static_cast<int64_t>(m.n_utts) * kCmvnThreadsPerUtt;
+  // a chain is sequential in t, so parallelism is n_utts * 20 threads: small batches run as
   // single-warp blocks spread over all SM sub-partitions instead of a few 5-warp blocks
-  const int block = threads >= static_cast<int64_t>(c->sm_count) * 4 * 160 ? 160 : 32;
+  const int block = threads >= static_cast<int64_t>(c->sm_count) * 2 * 160 ? 160 : 32;
   const int grid = static_cast<int>((threads + block - 1) / block);
-  // per-thread rings: x and x_old, kCmvnRing frames each
-  size_t dyn_smem = static_cast<size_t>(2) * kCmvnRing * block * sizeof(float);
+  // ring depth: 4 groups (32 frames); PKB_CMVN_GROUPS=8 doubles it (tuning knob)
+  static const int env_groups = getenv("PKB_CMVN_GROUPS") ? atoi(getenv("PKB_CMVN_GROUPS")) : 0;
+  const int groups = env_groups == 4 || env_groups == 8 ? env_groups : 4;
+  // per-thread rings: x and x_old pairs
+  size_t dyn_smem = static_cast<size_t>(2) * groups * kCmvnUnroll * block * sizeof(float2);
   // PKB_CMVN_BLOCKS_PER_SM=n (tuning knob): caps residency with unused dynamic shared memory
   static const int max_blocks = getenv("PKB_CMVN_BLOCKS_PER_SM") ? atoi(getenv("PKB_CMVN_BLOCKS_PER_SM")) : 0;
   if (max_blocks > 0) dyn_smem = std::max<size_t>(dyn_smem, (220 * 1024) / max_blocks - 6 * 1024);
@@ -332,15 +359,20 @@ int launch_cmvn(Ctx *c, const float *d_raw, const BatchMeta &m, float *d_out,
   const int n_planes = hi ? (lo ? 2 : 1) : 0;
   const bool fp16 = planes && planes->fp16;
   PKB_REQUIRE(!planes || planes->dim_pad == kMel, "cmvn: operand planes must have a row pitch of %d elements", kMel);
-#define PKB_CMVN_LAUNCH3(PL, FP, OUT, BLK)                                                               \
+#define PKB_CMVN_LAUNCH4(PL, FP, OUT, BLK, GR)                                                           \
   do {                                                                                                  \
     if (dyn_smem > 40 * 1024)                                                                           \
-      cudaFuncSetAttribute(cmvn_kernel<PL, FP, OUT, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                           static_cast<int>(dyn_smem));                                                 \
-    cmvn_kernel<PL, FP, OUT, BLK><<<grid, BLK, dyn_smem, c->stream>>>(                                  \
+      cudaFuncSetAttribute(cmvn_kernel<PL, FP, OUT, BLK, GR>,                                           \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem));    \
+    cmvn_kernel<PL, FP, OUT, BLK, GR><<<grid, BLK, dyn_smem, c->stream>>>(                              \
         d_raw, m.d_frame_off, m.d_num_frames, m.n_utts, c->cmvn_tab.as<float>(), d_out, hi, lo,         \
         planes ? planes->d_pad_off : nullptr, planes ? planes->left : 0, planes ? planes->right : 0,    \
         planes ? planes->dim_pad : 0);                                                                  \
+  } while (0)
+#define PKB_CMVN_LAUNCH3(PL, FP, OUT, BLK)                \
+  do {                                                    \
+    if (groups == 8) PKB_CMVN_LAUNCH4(PL, FP, OUT, BLK, 8); \
+    else PKB_CMVN_LAUNCH4(PL, FP, OUT, BLK, 4);             \
   } while (0)
 #define PKB_CMVN_LAUNCH2(PL, FP, OUT)                    \
   do {                                                   \
@@ -359,6 +391,7 @@ int launch_cmvn(Ctx *c, const float *d_raw, const BatchMeta &m, float *d_out,
   else if (n_planes == 2 && !fp16) PKB_CMVN_LAUNCH(2, false);
   else PKB_CMVN_LAUNCH(2, true);
 #undef PKB_CMVN_LAUNCH3
+#undef PKB_CMVN_LAUNCH4
 #undef PKB_CMVN_LAUNCH2
 #undef PKB_CMVN_LAUNCH
   PKB_CUDA(cudaGetLastError());

@@ -82,6 +82,10 @@ struct Ctx {
   // front-end tables
   DevBuf tables;
   FbankTables fb{};
+  // options the reference does not have (pkb_fbank_set_options); defaults = the reference
+  int window_type = PKB_WINDOW_HAMMING;
+  float dither = 0.0f;
+  uint64_t dither_seed = 0;
   // CMVN per-frame smoothing tables for the current global stats
   DevBuf cmvn_tab;           // float alpha[600], scale[600], global[41]
   float cmvn_global[PKB_CMVN_STATS_DIM] = {0};
@@ -121,10 +125,12 @@ struct BatchMeta {
   int64_t total_frames = 0;
   int n_tiles = 0;                      // fbank tiles of kFramesPerTile frames
   std::vector<int32_t> num_samples, num_frames, tile_prefix;
+  std::vector<int32_t> tile_utt;        // utterance of every fbank tile
   std::vector<int64_t> sample_off, frame_off;
   // device copies (one allocation)
   DevBuf dev;
   const int32_t *d_num_samples = nullptr, *d_num_frames = nullptr, *d_tile_prefix = nullptr;
+  const int32_t *d_tile_utt = nullptr;
   const int64_t *d_sample_off = nullptr, *d_frame_off = nullptr;
   int build_from_samples(const int32_t *ns, int n);
   int build_from_frames(const int32_t *nf, int n);

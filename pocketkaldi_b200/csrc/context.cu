@@ -100,6 +100,9 @@ static int finish_meta(BatchMeta *m) {
   m->total_samples = m->sample_off[n];
   m->total_frames = m->frame_off[n];
   m->n_tiles = m->tile_prefix[n];
+  m->tile_utt.resize(m->n_tiles);
+  for (int u = 0; u < n; ++u)
+    for (int32_t i = m->tile_prefix[u]; i < m->tile_prefix[u + 1]; ++i) m->tile_utt[i] = u;
   return PKB_OK;
 }
 
@@ -127,11 +130,12 @@ int BatchMeta::build_from_frames(const int32_t *nf, int n) {
 int BatchMeta::upload(cudaStream_t stream) {
   const size_t n1 = static_cast<size_t>(n_utts) + 1;
   // layout: int64 sample_off[n1], int64 frame_off[n1], int32 num_samples[n1], num_frames[n1], tile_prefix[n1]
-  const size_t bytes = n1 * (2 * sizeof(int64_t) + 3 * sizeof(int32_t));
+  const size_t bytes = n1 * (2 * sizeof(int64_t) + 3 * sizeof(int32_t)) + tile_utt.size() * sizeof(int32_t);
   std::vector<char> host(bytes);
   char *h = host.data();
   size_t o_so = 0, o_fo = o_so + n1 * 8, o_ns = o_fo + n1 * 8, o_nf = o_ns + n1 * 4,
-         o_tp = o_nf + n1 * 4;
+         o_tp = o_nf + n1 * 4, o_tu = o_tp + n1 * 4;
+  if (!tile_utt.empty()) memcpy(h + o_tu, tile_utt.data(), tile_utt.size() * 4);
   memcpy(h + o_so, sample_off.data(), n1 * 8);
   memcpy(h + o_fo, frame_off.data(), n1 * 8);
   if (n_utts) {
@@ -148,6 +152,7 @@ int BatchMeta::upload(cudaStream_t stream) {
   d_num_samples = reinterpret_cast<const int32_t *>(d + o_ns);
   d_num_frames = reinterpret_cast<const int32_t *>(d + o_nf);
   d_tile_prefix = reinterpret_cast<const int32_t *>(d + o_tp);
+  d_tile_utt = reinterpret_cast<const int32_t *>(d + o_tu);
   return PKB_OK;
 }
 
@@ -248,6 +253,22 @@ int pkb_sync(pkb_ctx_t *c) {
   PKB_CUDA(cudaSetDevice(c->device));
   PKB_CUDA(cudaStreamSynchronize(c->stream));
   return pkb::check_device_error(c, "pkb_sync");
+}
+
+int pkb_fbank_set_options(pkb_ctx_t *c, int window_type, float dither, uint64_t dither_seed) {
+  PKB_REQUIRE(c, "pkb_fbank_set_options: ctx is NULL");
+  PKB_REQUIRE(window_type == PKB_WINDOW_HAMMING || window_type == PKB_WINDOW_POVEY,
+              "pkb_fbank_set_options: unknown window type %d", window_type);
+  PKB_REQUIRE(dither >= 0.0f, "pkb_fbank_set_options: negative dither");
+  PKB_CUDA(cudaSetDevice(c->device));
+  PKB_CUDA(cudaStreamSynchronize(c->stream));  // kernels in flight read the window table
+  if (window_type != c->window_type) {
+    c->window_type = window_type;
+    PKB_TRY(pkb::build_fbank_tables(c));
+  }
+  c->dither = dither;
+  c->dither_seed = dither_seed;
+  return PKB_OK;
 }
 
 int pkb_device_sm_count(pkb_ctx_t *c) { return c ? c->sm_count : 0; }

@@ -5,8 +5,9 @@
 // ComputePowerSpectrum (:193-211), Melbanks::Compute (:165-184), floor + log (:244-245).
 //
 // Mapping. A block of 4 warps works on a tile of 8 consecutive frames of one
-// utterance; the tile's 1520 samples are staged once in shared memory. Half a
-// warp (16 lanes) owns one frame:
+// utterance, two frames per warp; the warps never synchronise with each other. Half a
+// warp (16 lanes) owns one frame and stages its 400 samples into the frame's own
+// shared-memory region (which later serves as the FFT transpose tile):
 //   * the 512-point real FFT is done, as in the reference, as a 256-point complex
 //     FFT of the packed signal plus a real post-pass; the 256 points are factored
 //     16 x 16: lane j runs a register-resident radix-16 DFT over points j + 16q,
@@ -32,9 +33,28 @@ namespace pkb {
 
 namespace {
 
-constexpr int kTileSamples = (kFramesPerTile - 1) * kShift + kFrame;  // 1520
+// per-frame shared region: 16 x 17 complex transpose tile (>= 400 staged samples, >= 256 power
+// values); 8 extra float2 make consecutive regions start 16 banks apart, so the 32-bit accesses
+// of the two half-warps of a warp never collide
 constexpr int kXStride = 17;                                          // padded transpose row
+constexpr int kXRegion = 16 * kXStride + 8;                           // float2 per frame
 constexpr int kPartSlots = 96;
+
+// Optional dither (not in the reference, default off): counter-based N(0,1) pair for the sample
+// pair `pair` of frame t of utterance u -- splitmix64 finaliser + Box-Muller.
+__device__ __forceinline__ float2 dither_pair(uint64_t seed, int u, int t, int pair) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(u) * 0x100000001B3ull +
+                                                static_cast<uint64_t>(t) * 1024ull + static_cast<uint64_t>(pair) + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u1 = (static_cast<float>(static_cast<uint32_t>(z >> 40)) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
+  const float u2 = static_cast<float>(static_cast<uint32_t>(z) >> 8) * (1.0f / 16777216.0f);            // [0, 1)
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -75,24 +95,22 @@ __host__ __device__ constexpr int bin_of_reg(int r) { return (r >> 2) + 4 * (r &
 __host__ __device__ constexpr int reg_of_bin(int k) { return 4 * (k & 3) + (k >> 2); }
 
 template <typename SampleT>
-// 7 blocks (28 warps) per SM: 72 registers and 31 KB of shared memory per block. The FFT twiddle
-// tables are read through L1 (__ldg) instead of being staged: 4 KB less shared memory buys the
-// seventh block (measured 1.072 M -> 1.034 M cycles per 511 k frames; moving the Hamming and mel
-// tables out as well for an eighth block was slower again).
+// 7 blocks (28 warps) per SM: 72 registers and 25 KB of shared memory per block. The FFT twiddle
+// tables are read through L1 (__ldg) instead of being staged (measured 1.072 M -> 1.034 M
+// cycles per 511 k frames when that bought the seventh block).
 __global__ void __launch_bounds__(128, 7)
 fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample_off,
              const int32_t *__restrict__ num_samples, const int32_t *__restrict__ num_frames,
              const int64_t *__restrict__ frame_off, const int32_t *__restrict__ tile_prefix,
-             int n_utts, int n_tiles, FbankTables tab, float *__restrict__ out) {
-  __shared__ __align__(16) float s_pcm[kTileSamples];
+             const int32_t *__restrict__ tile_utt, int n_tiles, FbankTables tab, float *__restrict__ out,
+             float dither, uint64_t dither_seed) {
   __shared__ __align__(16) float s_ham[kFrame];
   __shared__ float4 s_melw[128];
   __shared__ uint32_t s_melb[128];
   __shared__ uint32_t s_melc[32];
   __shared__ uint32_t s_mels[kMel];
-  __shared__ __align__(16) float2 s_x[4][2][16 * kXStride];  // per warp, per frame: transpose tile, then power
+  __shared__ __align__(16) float2 s_x[4][2][kXRegion];  // per warp, per frame: samples, transpose tile, power
   __shared__ float s_part[4][2][kPartSlots];
-  __shared__ int s_utt;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -103,58 +121,46 @@ fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample
   s_melb[tid] = tab.mel_bins[tid];
   if (tid < 32) s_melc[tid] = tab.mel_ctl[tid];
   if (tid < kMel) s_mels[tid] = tab.mel_sum[tid];
+  __syncthreads();  // the only block-wide barrier: the tables are staged
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    __syncthreads();  // previous tile finished with s_pcm / s_utt; table staging visible
-    if (tid == 0) {
-      // utterance of this tile: largest u with tile_prefix[u] <= tile (one search per block)
-      int lo = 0, hi = n_utts - 1;
-      while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
-      }
-      s_utt = lo;
-    }
-    __syncthreads();
-    const int u = s_utt;
+    const int u = __ldg(tile_utt + tile);
     const int t0 = (tile - tile_prefix[u]) * kFramesPerTile;
     const int T = num_frames[u];
-    const int n = num_samples[u];
-    const SampleT *src = pcm + sample_off[u];
-    const int s0 = t0 * kShift;
-    // 16-byte vector loads (8 int16 / 4 float samples) when the tile start is aligned and the
-    // whole tile lies inside the utterance; element-wise otherwise
-    constexpr int kVec = 16 / sizeof(SampleT);
-    const bool vec_ok = (s0 + kTileSamples <= n) &&
-                        ((reinterpret_cast<uintptr_t>(src + s0) & 15) == 0);
-    if (vec_ok) {
-      const uint4 *v = reinterpret_cast<const uint4 *>(src + s0);
-      for (int i = tid; i < kTileSamples / kVec; i += 128) {
-        const uint4 w = __ldg(v + i);
-        float *d = s_pcm + i * kVec;
-        if (sizeof(SampleT) == 2) {
-          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            d[2 * q] = static_cast<float>(static_cast<int16_t>(ww[q] & 0xffffu));
-            d[2 * q + 1] = static_cast<float>(static_cast<int16_t>(ww[q] >> 16));
-          }
-        } else {
-          *reinterpret_cast<uint4 *>(d) = w;
-        }
-      }
-    } else {
-      for (int i = tid; i < kTileSamples; i += 128) {
-        int s = s0 + i;
-        s_pcm[i] = s < n ? static_cast<float>(src[s]) : 0.0f;
-      }
-    }
-    __syncthreads();
-
     const int f = warp * 2 + half;  // frame inside the tile
     const int t = t0 + f;
     const bool valid = t < T;
-    const float *x = s_pcm + f * kShift;
+    float2 *xb = s_x[warp][half];
+    float *x = reinterpret_cast<float *>(xb);
+
+    // ---- stage this frame's 400 samples (src/fbank.cc:74-100: they always lie inside the
+    //      utterance, T = 1 + (n - 400) / 160). 16-byte vector loads when the frame start is aligned.
+    if (valid) {
+      const SampleT *fs = pcm + sample_off[u] + static_cast<int64_t>(t) * kShift;
+      constexpr int kVec = 16 / sizeof(SampleT);
+      if ((reinterpret_cast<uintptr_t>(fs) & 15) == 0) {
+        const uint4 *v = reinterpret_cast<const uint4 *>(fs);
+        for (int i = j; i < kFrame / kVec; i += 16) {
+          const uint4 w = __ldg(v + i);
+          if (sizeof(SampleT) == 2) {
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            float d[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              d[2 * q] = static_cast<float>(static_cast<int16_t>(ww[q] & 0xffffu));
+              d[2 * q + 1] = static_cast<float>(static_cast<int16_t>(ww[q] >> 16));
+            }
+            *reinterpret_cast<float4 *>(x + i * 8) = make_float4(d[0], d[1], d[2], d[3]);
+            *reinterpret_cast<float4 *>(x + i * 8 + 4) = make_float4(d[4], d[5], d[6], d[7]);
+          } else {
+            *reinterpret_cast<uint4 *>(x + i * 4) = w;
+          }
+        }
+      } else {
+        for (int i = j; i < kFrame; i += 16) x[i] = static_cast<float>(fs[i]);
+      }
+    }
+    __syncwarp();
 
     // ---- window: DC removal, pre-emphasis, Hamming (src/fbank.cc:44-69) ----
     float2 a[16];
@@ -168,11 +174,18 @@ fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample
       if (q < 12 || j < 8) {
         v = *reinterpret_cast<const float2 *>(x + 2 * m);
         p = x[m == 0 ? 0 : 2 * m - 1];
+        if (dither != 0.0f) {
+          const float2 n = dither_pair(dither_seed, u, t, m);
+          v.x = fmaf(dither, n.x, v.x);
+          v.y = fmaf(dither, n.y, v.y);
+          p = m == 0 ? v.x : fmaf(dither, dither_pair(dither_seed, u, t, m - 1).y, p);
+        }
       }
       a[q] = v;
       xm1[q] = p;
       sum += v.x + v.y;
     }
+    __syncwarp();  // every lane has read its samples: the region becomes the transpose tile
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, 16);
     const float mean = sum / static_cast<float>(kFrame);
@@ -191,7 +204,6 @@ fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample
 
     // ---- 256-point complex FFT = 16 x 16 ----
     dft16(a);
-    float2 *xb = s_x[warp][half];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const int k1 = bin_of_reg(r);
@@ -288,8 +300,7 @@ fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample
         }
       }
     }
-    (void)valid;
-    __syncwarp();
+    __syncwarp();  // the next tile's staging overwrites the power values
   }
 }
 
@@ -303,8 +314,8 @@ int launch_fbank(Ctx *c, const SampleT *d_pcm, const BatchMeta &m, float *d_raw)
   LaunchScope scope(c, PKB_KERNEL_FBANK);
   fbank_kernel<SampleT><<<grid, 128, 0, c->stream>>>(d_pcm, m.d_sample_off, m.d_num_samples,
                                                      m.d_num_frames, m.d_frame_off,
-                                                     m.d_tile_prefix, m.n_utts, m.n_tiles, c->fb,
-                                                     d_raw);
+                                                     m.d_tile_prefix, m.d_tile_utt, m.n_tiles, c->fb,
+                                                     d_raw, c->dither, c->dither_seed);
   PKB_CUDA(cudaGetLastError());
   return PKB_OK;
 }
@@ -326,13 +337,15 @@ float mel_scale(float f) { return 1127.0f * logf(1.0f + f / 700.0f); }  // src/f
 }  // namespace
 
 int build_fbank_tables(Ctx *c) {
-  // Hamming window, src/fbank.cc:249-256 (M_2PI is 6.28318530718 there, fbank.cc:18-20)
+  // Hamming window, src/fbank.cc:249-256 (M_2PI is 6.28318530718 there, fbank.cc:18-20).
+  // PKB_WINDOW_POVEY (not in the reference, off by default): Kaldi's pow(0.5 - 0.5 cos, 0.85).
   std::vector<float> ham(kFrame);
   {
     float a = 6.28318530718 / (kFrame - 1);
     for (int i = 0; i < kFrame; ++i) {
       float i_fl = static_cast<float>(i);
-      ham[i] = 0.54 - 0.46 * cos(a * i_fl);
+      if (c->window_type == PKB_WINDOW_POVEY) ham[i] = pow(0.5 - 0.5 * cos(a * i_fl), 0.85);
+      else ham[i] = 0.54 - 0.46 * cos(a * i_fl);
     }
   }
   // exact twiddles

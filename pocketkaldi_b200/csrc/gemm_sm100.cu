@@ -733,9 +733,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               z[i + 2] = fmaf(__uint_as_float(v[i + 2]), rs, b.z);
               z[i + 3] = fmaf(__uint_as_float(v[i + 3]), rs, b.w);
             }
-            if (p.relu) {
+            if (p.relu == 1) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) z[i] = fmaxf(z[i], 0.0f);
+            } else if (p.relu == 2) {  // sigmoid (not a reference layer type; parity unpinned)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) z[i] = 1.0f / (1.0f + expf(-z[i]));
             }
             if (p.out_sumsq != nullptr) {
 #pragma unroll

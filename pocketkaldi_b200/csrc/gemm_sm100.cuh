@@ -46,7 +46,7 @@ struct GemmParams {
   int in_sumsq_tiles;
   float in_dim;        // D of the NormalizeLayer feeding this stage
   float *out_sumsq;    // [M][n_tiles_n * sumsq_parts(planes)] or nullptr
-  int relu;
+  int relu;            // activation behind the linear layer: 0 none, 1 ReLU, 2 sigmoid
   int fp16;            // operands (and hidden outputs) are FP16 instead of BF16
   __nv_bfloat16 *out_hi, *out_lo;  // [M][ld_out]
   int ld_out;

@@ -286,18 +286,19 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
     ++lin;
     ++i;
     if (i < n_layers && types[i] == 1) { st.relu = true; ++i; }
+    else if (i < n_layers && types[i] == PKB_LAYER_SIGMOID) { st.sigmoid = true; ++i; }
     if (i < n_layers && types[i] == 2) { st.normalize = true; ++i; }
     if (i < n_layers && types[i] == 3) { am->softmax_last = true; ++i; }
     if (i < n_layers && types[i] != 0 && rc == PKB_OK) {
-      set_error("layer %d: type %d in an unsupported position (supported: linear [relu] "
+      set_error("layer %d: type %d in an unsupported position (supported: linear [relu | sigmoid] "
                 "[normalize] ... linear [softmax])", i, types[i]);
       rc = PKB_ERR_UNSUPPORTED;
     }
   }
   if (rc == PKB_OK) {
     const Stage &last = am->stages.back();
-    if (last.relu || last.normalize) {
-      set_error("relu / normalize after the last linear layer is not supported");
+    if (last.relu || last.sigmoid || last.normalize) {
+      set_error("relu / sigmoid / normalize after the last linear layer is not supported");
       rc = PKB_ERR_UNSUPPORTED;
     }
   }
@@ -334,6 +335,7 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
                       am->planes, am->fp16);
       if (rc == PKB_OK) {
         am->splice_stage.relu = am->stages[0].relu;
+        am->splice_stage.sigmoid = am->stages[0].sigmoid;
         am->splice_stage.normalize = am->stages[0].normalize;
         am->has_splice_stage = true;
       }
@@ -434,7 +436,7 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
     p.in_sumsq = in_sumsq;
     p.in_sumsq_tiles = in_sumsq_tiles;
     p.in_dim = in_dim;
-    p.relu = st.relu ? 1 : 0;
+    p.relu = st.relu ? 1 : (st.sigmoid ? 2 : 0);
     p.fp16 = am->fp16;
     if (!final) {
       const int buf = static_cast<int>(i & 1);

@@ -15,6 +15,7 @@ struct Stage {
   int k_pad = 0, n_pad = 0;     // K padded to 64, N padded to block_n
   int block_n = 128;
   bool relu = false;            // ReLULayer follows       (src/nnet.cc:49-60)
+  bool sigmoid = false;         // sigmoid follows (PKB_LAYER_SIGMOID; not a reference layer type)
   bool normalize = false;       // NormalizeLayer follows  (src/nnet.cc:62-75)
   DevBuf w_hi, w_lo, bias;      // [n_pad][k_pad] BF16 planes, [n_pad] FP32
   CUtensorMap tm_w_hi, tm_w_lo;

@@ -22,7 +22,9 @@ import numpy as np
 
 LINEAR, RELU, NORMALIZE, SOFTMAX = 0, 1, 2, 3
 MUL = 5  # tool/convert_am.py:16-22; not in the reference reader's enum (src/nnet.h)
-LAYER_NAMES = {LINEAR: "linear", RELU: "relu", NORMALIZE: "normalize", SOFTMAX: "softmax"}
+SIGMOID = 6  # PKB_LAYER_SIGMOID: not a reference layer type at all (north_star option, parity unpinned)
+LAYER_NAMES = {LINEAR: "linear", RELU: "relu", NORMALIZE: "normalize", SOFTMAX: "softmax",
+               SIGMOID: "sigmoid"}
 FST_SECTION = b"pk::fst_0"
 
 

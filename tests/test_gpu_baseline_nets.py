@@ -45,7 +45,7 @@ def reference_loglik(reference, cfg, pcms, g, tmp_path):
     return layers, prior, feats, lls
 
 
-@pytest.mark.parametrize("config,n_utts", [("3", 3), ("4", 1)])
+@pytest.mark.parametrize("config,n_utts", [("3", 3), ("4", 3)])
 def test_headline_precision_meets_the_parity_bar(ctx, reference, tmp_path, config, n_utts):
     if reference is None:
         pytest.skip("oracle/_ref/libpkref.so not built")

@@ -59,10 +59,11 @@ def test_words_identical_to_reference(wavs, toy_conf):
     if not os.path.exists(SHIM_CLI):
         pytest.skip("oracle/_ref/pocketkaldi_b200_cli not built (needs /root/reference at build time)")
     gold = golden_hyps()
-    for name in ("hello", "cat"):
-        (_, hyp, llpf), = run_cli(SHIM_CLI, toy_conf, wavs[name], {"PKB_PRECISION": "bf16x3"})
-        assert hyp == gold[name][0], (name, hyp, gold[name][0])
-        assert abs(llpf - gold[name][1]) < 2e-3
+    for prec in ("bf16x3", "fp16c8", "fp16x3"):   # every mode that meets the parity bar
+        for name in ("hello", "cat"):
+            (_, hyp, llpf), = run_cli(SHIM_CLI, toy_conf, wavs[name], {"PKB_PRECISION": prec})
+            assert hyp == gold[name][0], (prec, name, hyp, gold[name][0])
+            assert abs(llpf - gold[name][1]) < 2e-3
     # .scp input (src/main.cc:34-46)
     res = run_cli(SHIM_CLI, toy_conf, wavs["scp"], {"PKB_PRECISION": "bf16x3"})
     assert [r[1] for r in res] == [gold["hello"][0], gold["cat"][0]]

@@ -138,6 +138,7 @@ def main():
         "fp16 hidden X3, last S": ("fp16", [X3] * H + [S]),
         "fp16x3": ("fp16", [X3] * n_lin),
         "fp16+c8 all": ("fp16", [C] * n_lin),
+        "fp16c8 (first layer X3)": ("fp16", [X3] + [C] * (n_lin - 1)),
         "fp16+c8 hidden, last S": ("fp16", [C] * H + [S]),
         "fp16+c8 hid, last Wc": ("fp16", [C] * H + [(1, "c")]),
         "fp16+c8 hid, last Ac": ("fp16", [C] * H + [("c", 1)]),

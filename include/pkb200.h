@@ -242,6 +242,31 @@ int pkb_batch_set_compact(pkb_batch_t *batch, int on);
  * Does not touch the GPU. */
 int pkb_loglik16_expand(const uint16_t *h, const float *off, int64_t n_frames, int num_pdfs,
                         float prob_scale, float *out);
+/* ---- GPU Viterbi ----------------------------------------------------------
+ * Decoder::Decode + BestPath (src/decoder.cc:39-339) over an Fst (src/fst.cc:29-129) for every
+ * utterance of a batch, one thread block per utterance, reading the log-likelihood rows where
+ * pkb_batch_run left them in HBM: the [frames x pdfs] matrix never crosses PCIe and no host core
+ * walks it. Costs, the beam (16 in the reference) and the best-path rule are the reference's;
+ * differences (tightest instead of running cutoff, hard token capacity instead of the sampled
+ * max-active estimate, tie-breaking) are listed in pocketkaldi_b200/csrc/decoder.cu. */
+typedef struct pkb_fst pkb_fst_t;
+/* Fst::Read (src/fst.cc:29-92): "pk::fst_0" file. */
+int pkb_fst_load(pkb_ctx_t *ctx, const char *path, pkb_fst_t **fst);
+/* Same from memory: final[num_states], first_arc[num_states] (-1: no arcs), and num_arcs arcs of
+ * four 32-bit words {next_state, input_label, output_label, weight (float bits)} sorted by
+ * source state -- the file's own layout. */
+int pkb_fst_create(pkb_ctx_t *ctx, int num_states, int start_state, const float *final_weights,
+                   const int32_t *first_arc, int num_arcs, const int32_t *arcs, pkb_fst_t **fst);
+void pkb_fst_destroy(pkb_fst_t *fst);
+/* Decodes every utterance of the batch from its FP32 log-likelihood buffer (the nnet stage must
+ * have run with the compact output off; the model needs its tid2pdf map). beam <= 0 selects the
+ * reference's 16. words_out: [n_utts][max_words] output labels in spoken order; n_words_out[u] =
+ * number of words of utterance u (it may exceed max_words: the list is then truncated), or a
+ * negative code when the search ran out of its per-utterance capacity (max_tokens tokens per
+ * frame; 0 selects 4096); weight_out[u] = Hypothesis::weight(). Synchronous. */
+int pkb_batch_decode(pkb_batch_t *batch, const pkb_fst_t *fst, float beam, int max_tokens,
+                     int max_words, int32_t *words_out, int32_t *n_words_out, float *weight_out);
+
 /* Sum over all elements of a per-frame float buffer, computed on the device
  * in double (a cheap whole-output fingerprint for full-size runs). */
 int pkb_batch_checksum(pkb_batch_t *batch, int which, double *sum_out);

@@ -95,6 +95,10 @@ _SIGNATURES = [
     ("pkb_batch_get_rows", C.c_int, [_VP, C.c_int, C.c_int64, C.c_int64, _VP]),
     ("pkb_batch_checksum", C.c_int, [_VP, C.c_int, C.POINTER(C.c_double)]),
     ("pkb_batch_set_compact", C.c_int, [_VP, C.c_int]),
+    ("pkb_fst_load", C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
+    ("pkb_fst_create", C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, C.c_int, _VP, C.POINTER(_VP)]),
+    ("pkb_fst_destroy", None, [_VP]),
+    ("pkb_batch_decode", C.c_int, [_VP, _VP, C.c_float, C.c_int, C.c_int, _VP, _VP, _VP]),
     ("pkb_loglik16_expand", C.c_int, [_VP, _VP, C.c_int64, C.c_int, C.c_float, _VP]),
     ("pkb_stream_create", C.c_int, [_VP, _VP, C.c_int, C.c_int, _f32p, C.c_float, C.POINTER(_VP)]),
     ("pkb_stream_destroy", None, [_VP]),
@@ -637,6 +641,18 @@ class Batch:
             return (self.total_frames,), np.float32
         return (self.total_frames, self.am.num_pdfs()), np.float32
 
+    def decode(self, fst, beam=0.0, max_tokens=0, max_words=256):
+        """GPU Viterbi over the batch's FP32 log-likelihoods (pkb_batch_decode): returns
+        ([word id lists in spoken order], weights); a failed search gives None for its utterance."""
+        n = len(self.num_samples)
+        words = np.zeros((max(n, 1), max_words), np.int32)
+        nw = np.zeros(max(n, 1), np.int32)
+        wt = np.zeros(max(n, 1), np.float32)
+        _check(self.ctx.lib.pkb_batch_decode(self.h, fst.h, beam, max_tokens, max_words, words.ctypes.data,
+                                             nw.ctypes.data, wt.ctypes.data))
+        hyps = [None if nw[u] < 0 else [int(x) for x in words[u, :min(int(nw[u]), max_words)]] for u in range(n)]
+        return hyps, wt[:n].copy()
+
     def set_compact(self, on=True):
         """Half-size output of the nnet stage (see pkb_batch_set_compact in include/pkb200.h)."""
         _check(self.ctx.lib.pkb_batch_set_compact(self.h, 1 if on else 0))
@@ -665,6 +681,46 @@ class Batch:
         s = C.c_double(0)
         _check(self.ctx.lib.pkb_batch_checksum(self.h, which, C.byref(s)))
         return s.value
+
+
+class Fst:
+    """pocketkaldi::Fst (src/fst.cc:29-129) resident on the GPU for Batch.decode."""
+
+    def __init__(self, ctx, path=None, graph=None):
+        """path: a "pk::fst_0" file, or graph = (num_states, start, {state: final weight},
+        [(src, dst, ilabel, olabel, weight)]) as pocketkaldi_b200.formats.write_fst takes it."""
+        self.ctx = ctx
+        self.h = _VP()
+        if path is not None:
+            _check(ctx.lib.pkb_fst_load(ctx.h, path.encode(), C.byref(self.h)))
+        else:
+            ns, start, finals, arcs = graph
+            arcs = sorted(arcs)
+            first = np.full(ns, -1, np.int32)
+            for i, a in enumerate(arcs):
+                if first[a[0]] == -1:
+                    first[a[0]] = i
+            fin = np.full(ns, np.inf, np.float32)
+            for st, wgt in finals.items():
+                fin[st] = wgt
+            raw = np.zeros((max(len(arcs), 1), 4), np.int32)
+            for i, a in enumerate(arcs):
+                raw[i, :3] = (a[1], a[2], a[3])
+                raw[i, 3] = np.float32(a[4]).view(np.int32)
+            _check(ctx.lib.pkb_fst_create(ctx.h, ns, start, fin.ctypes.data, first.ctypes.data, len(arcs),
+                                          raw.ctypes.data, C.byref(self.h)))
+        ctx._adopt(self)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.pkb_fst_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Stream:

@@ -12,6 +12,7 @@
 #include <memory>
 #include <string>
 
+#include "decoder.cuh"
 #include "nnet.cuh"
 
 using pkb::BatchMeta;
@@ -279,6 +280,7 @@ struct pkb_batch {
   pkb::DevBuf pcm, raw, feats, loglik, sum;
   bool compact = false;             // nnet stage writes loglik16 + loglik_off instead of loglik
   pkb::DevBuf loglik16, loglik_off;
+  pkb::DevBuf vit_work, vit_out, vit_tid2pdf;  // GPU Viterbi: workspace, results, device tid2pdf
   Workspace ws;
   pkb::PaddedPlanes planes;
   int64_t padded = 0, gemm_rows = 0;
@@ -634,6 +636,9 @@ void pkb_batch_destroy(pkb_batch_t *b) {
   b->loglik.release();
   b->loglik16.release();
   b->loglik_off.release();
+  b->vit_work.release();
+  b->vit_out.release();
+  b->vit_tid2pdf.release();
   b->sum.release();
   b->ws.release();
   b->meta.dev.release();
@@ -819,6 +824,92 @@ int pkb_batch_checksum(pkb_batch_t *b, int which, double *sum_out) {
   PKB_CUDA(cudaMemcpyAsync(sum_out, b->sum.p, sizeof(double), cudaMemcpyDeviceToHost, b->c->stream));
   PKB_CUDA(cudaStreamSynchronize(b->c->stream));
   return pkb::check_device_error(b->c, "pkb_batch_checksum");
+}
+
+// ---------------------------------------------------------------- GPU Viterbi
+int pkb_fst_create(pkb_ctx_t *c, int num_states, int start_state, const float *final_weights,
+                   const int32_t *first_arc, int num_arcs, const int32_t *arcs, pkb_fst_t **fst) {
+  PKB_REQUIRE(c && fst, "pkb_fst_create: NULL argument");
+  *fst = nullptr;
+  PKB_CUDA(cudaSetDevice(c->device));
+  return pkb::fst_build(c, num_states, start_state, final_weights, first_arc, num_arcs, arcs, fst);
+}
+
+int pkb_fst_load(pkb_ctx_t *c, const char *path, pkb_fst_t **fst) {
+  PKB_REQUIRE(c && path && fst, "pkb_fst_load: NULL argument");
+  *fst = nullptr;
+  File fd;
+  PKB_TRY(fd.open(path));
+  // Fst::Read, src/fst.cc:29-92
+  char name[32];
+  PKB_TRY(fd.read(name, 32));
+  name[31] = 0;
+  if (strcmp(name, "pk::fst_0") != 0) {
+    pkb::set_error("Corruption: section_name == 'pk::fst_0' expected, but '%s' found", name);
+    return PKB_ERR_CORRUPT;
+  }
+  int32_t size = 0, ns = 0, na = 0, start = 0;
+  PKB_TRY(fd.read_i32(&size));
+  PKB_TRY(fd.read_i32(&ns));
+  PKB_TRY(fd.read_i32(&na));
+  PKB_TRY(fd.read_i32(&start));
+  const int64_t expect = 12 + static_cast<int64_t>(ns) * 8 + static_cast<int64_t>(na) * 16;
+  if (ns < 0 || na < 0 || expect != size) {
+    pkb::set_error("Corruption: section_size == %lld expected, but %d found", static_cast<long long>(expect), size);
+    return PKB_ERR_CORRUPT;
+  }
+  std::vector<float> fin(ns);
+  std::vector<int32_t> first(ns), arcs(static_cast<size_t>(na) * 4);
+  if (ns) PKB_TRY(fd.read(fin.data(), sizeof(float) * ns));
+  if (ns) PKB_TRY(fd.read(first.data(), sizeof(int32_t) * ns));
+  if (na) PKB_TRY(fd.read(arcs.data(), sizeof(int32_t) * 4 * static_cast<size_t>(na)));
+  return pkb_fst_create(c, ns, start, fin.data(), first.data(), na, arcs.data(), fst);
+}
+
+void pkb_fst_destroy(pkb_fst_t *fst) {
+  if (!fst) return;
+  if (fst->c) cudaSetDevice(fst->c->device);
+  fst->buf.release();
+  delete fst;
+}
+
+int pkb_batch_decode(pkb_batch_t *b, const pkb_fst_t *fst, float beam, int max_tokens, int max_words,
+                     int32_t *words_out, int32_t *n_words_out, float *weight_out) {
+  PKB_REQUIRE(b && fst, "pkb_batch_decode: NULL argument");
+  PKB_REQUIRE(b->am, "pkb_batch_decode: the batch has no model");
+  PKB_REQUIRE(fst->c == b->c, "pkb_batch_decode: the FST belongs to another context");
+  PKB_REQUIRE(!b->compact, "pkb_batch_decode: reads the FP32 log-likelihoods (switch the compact output off)");
+  PKB_REQUIRE(!b->am->tid2pdf.empty(), "pkb_batch_decode: the model has no tid2pdf map");
+  PKB_REQUIRE(max_words > 0 && words_out && n_words_out && weight_out, "pkb_batch_decode: bad output arguments");
+  Ctx *c = b->c;
+  PKB_CUDA(cudaSetDevice(c->device));
+  const int n = b->meta.n_utts;
+  if (n == 0) return PKB_OK;
+  pkb::ViterbiConfig cfg;
+  if (beam > 0.0f) cfg.beam = beam;
+  if (max_tokens > 0) cfg.max_tokens = max_tokens;
+  cfg.max_words = max_words;
+  pkb_am *am = b->am;
+  const size_t tid_bytes = am->tid2pdf.size() * sizeof(int32_t);
+  if (b->vit_tid2pdf.cap < tid_bytes) {
+    PKB_TRY(b->vit_tid2pdf.ensure(tid_bytes));
+    PKB_CUDA(cudaMemcpyAsync(b->vit_tid2pdf.p, am->tid2pdf.data(), tid_bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  const size_t words_bytes = static_cast<size_t>(n) * max_words * sizeof(int32_t);
+  const size_t out_bytes = words_bytes + static_cast<size_t>(n) * (sizeof(int32_t) + sizeof(float));
+  PKB_TRY(b->vit_out.ensure(out_bytes));
+  int32_t *d_words = b->vit_out.as<int32_t>();
+  int32_t *d_nw = reinterpret_cast<int32_t *>(b->vit_out.as<char>() + words_bytes);
+  float *d_wt = reinterpret_cast<float *>(d_nw + n);
+  PKB_CUDA(cudaMemsetAsync(b->vit_out.p, 0, out_bytes, c->stream));
+  PKB_TRY(pkb::launch_viterbi(c, fst, cfg, b->loglik.as<float>(), am->num_pdfs, b->ws.pad_off.as<int64_t>(),
+                              b->meta.d_num_frames, n, b->vit_tid2pdf.as<int32_t>(),
+                              static_cast<int>(am->tid2pdf.size()), &b->vit_work, d_words, d_nw, d_wt));
+  PKB_CUDA(cudaMemcpyAsync(words_out, d_words, words_bytes, cudaMemcpyDeviceToHost, c->stream));
+  PKB_CUDA(cudaMemcpyAsync(n_words_out, d_nw, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  PKB_CUDA(cudaMemcpyAsync(weight_out, d_wt, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+  PKB_CUDA(cudaStreamSynchronize(c->stream));
+  return pkb::check_device_error(c, "pkb_batch_decode");
 }
 
 // ---------------------------------------------------------------- fused host path

@@ -256,21 +256,27 @@ fbank_kernel(const SampleT *__restrict__ pcm, const int64_t *__restrict__ sample
     __syncwarp();
 
     // ---- mel filterbank, floor, log (fbank.cc:165-184, :244-245) ----
+    // this lane's 16 (weight, bin) entries are the same for both frames of the warp: one load
+    float wv[16];
+    uint32_t bb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 w = s_melw[q * 32 + lane];
+      wv[4 * q] = w.x; wv[4 * q + 1] = w.y; wv[4 * q + 2] = w.z; wv[4 * q + 3] = w.w;
+      bb[q] = s_melb[q * 32 + lane];
+    }
+    const uint32_t ctl = s_melc[lane];
 #pragma unroll
     for (int fr = 0; fr < 2; ++fr) {
       const float *pf = reinterpret_cast<const float *>(s_x[warp][fr]);
       float *part = s_part[warp][fr];
-      const uint32_t ctl = s_melc[lane];
       uint32_t slot = ctl >> 16;
       float acc = 0.0f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 w = s_melw[q * 32 + lane];
-        const uint32_t b = s_melb[q * 32 + lane];
-        const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          acc = fmaf(wv[i], pf[(b >> (8 * i)) & 0xffu], acc);
+          acc = fmaf(wv[4 * q + i], pf[(bb[q] >> (8 * i)) & 0xffu], acc);
           if ((ctl >> (4 * q + i)) & 1u) {
             part[slot++] = acc;
             acc = 0.0f;

@@ -311,9 +311,10 @@ def test_loader_errors_follow_the_reference_convention(ctx, tmp_path, toy_conf):
         pk.AcousticModel(ctx).Read(conf)
     assert e.value.code == 3 and "Unable to find key 'prior'" in str(e.value)
     # unknown layer types are rejected like the reference reader does (src/nnet.cc:122-126);
-    # MUL (5) is the one extension, see test_mul_layers_are_folded_into_linear
+    # MUL (5) and the optional sigmoid (6, tests/test_gpu_options.py) are the extensions, see
+    # test_mul_layers_are_folded_into_linear
     import struct
-    for bad_type in (4, 6, -1):
+    for bad_type in (4, 7, -1):
         with open(d / "bad.nnet", "wb") as fd:
             fd.write(b"NNT0" + struct.pack("<ii", 4, 1) + b"LAY0" + struct.pack("<ii", 4, bad_type))
         open(conf, "w").writelines([l.replace("toy.nnet", "bad.nnet") if l.startswith("nnet") else l

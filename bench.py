@@ -393,6 +393,9 @@ def run_gpu_arm(args, cfg):
 
     # ---- end to end through the host-buffer API: pinned PCM in, log-likelihoods out, per chunk
     e2e = None if args.no_e2e else run_e2e(env, cfg, am, n_utts, batch)
+    e2e_decode = None
+    if cfg["nnet"] and not args.no_e2e:
+        e2e_decode = run_e2e_decode(env, cfg, n_utts)
 
     # ---- parity sample (rank 0) and CPU baseline (rank 0, N=1 only)
     cpu = parity = other_modes = None
@@ -445,6 +448,7 @@ def run_gpu_arm(args, cfg):
             "kernel_ms_per_step": main["kernel_ms_per_step"],
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "e2e_decode": e2e_decode,
             "gpu_launches": main["gpu_launches"],
             "clocks": main["clocks"],
             "checksum": main["checksum"],
@@ -580,6 +584,62 @@ def run_e2e(env, cfg, am, n_utts, main_batch=None):
             "finite": fin, "timing": "host wall clock over both streams (>= the CUDA-event time of stream 0)",
             "api": "2 x (pkb_batch_set_pcm_i16 + pkb_batch_run + pkb_batch_get_rows), pinned host "
                    "buffers, two contexts alternating so D2H overlaps the next chunk"}
+
+
+def run_e2e_decode(env, cfg, n_utts):
+    """PCM in pinned host memory -> H2D -> fbank/CMVN/nnet -> GPU Viterbi (pkb_batch_decode) -> word
+    ids on the host: the path on which the [frames x pdfs] matrix never crosses PCIe.
+    Graph: the 40-word loop of tools/decode_demo.py over the config's pdfs; beam 16 like the
+    reference decoder. One context, chunk after chunk (the decode call synchronises)."""
+    import pocketkaldi_b200 as pk
+    from pocketkaldi_b200.binding import PinnedArray
+    from pocketkaldi_b200.synth import synth_pcm
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from decode_demo import word_loop_graph
+    args, ctx, rank, local, dist = env.args, env.ctx, env.rank, env.local, env.dist
+    chunk = min(args.e2e_chunk, n_utts)
+    n_chunks = max(n_utts // chunk, 1)
+    graph, tid2pdf = word_loop_graph(40, 3, cfg["pdfs"])
+    am = pk.AcousticModel(ctx, precision_id(args.precision)).from_layers(
+        make_layers(cfg), uniform_prior(cfg), 5, 5, tid2pdf=np.asarray(tid2pdf, np.int32))
+    fst = pk.Fst(ctx, graph=graph)
+    cb = pk.Batch(ctx, [SAMPLES_10S] * chunk, env.g, am, prob_scale=0.1)
+    pin_in = PinnedArray((chunk * SAMPLES_10S,), np.int16)
+    pin_in.array[:] = synth_pcm(1234, np.arange(chunk) + rank * n_utts, SAMPLES_10S).reshape(-1)
+    stages = pk.STAGE_ALL | pk.STAGE_NO_FEATS
+    words = 0
+
+    def step():
+        nonlocal words
+        for _ in range(n_chunks):
+            cb.set_pcm(pin_in.array)
+            cb.run(stages)
+            hyps, _ = cb.decode(fst)
+            words = sum(len(h) for h in hyps if h is not None)
+            if any(h is None for h in hyps):
+                raise RuntimeError("GPU Viterbi ran out of token capacity")
+
+    step()
+    barrier(dist, local)
+    steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    ms = (time.perf_counter() - t0) * 1e3
+    barrier(dist, local)
+    ms_max, frames = reduce_timing(dist, local, ms, cb.total_frames * n_chunks)
+    res = {"value": frames * steps / (ms_max * 1e-3), "unit": "frames/s", "steps": steps,
+           "ms_per_step": ms_max / steps, "chunk_utts": chunk, "chunks_per_step": n_chunks,
+           "h2d_bytes_per_step": int(pin_in.array.nbytes * n_chunks),
+           "d2h_bytes_per_step": int(chunk * (256 + 2) * 4 * n_chunks),
+           "words_per_chunk": int(words),
+           "graph": "40-word loop, 121 states, 1800 arcs, beam 16 (tools/decode_demo.py)",
+           "api": "pkb_batch_set_pcm_i16 + pkb_batch_run + pkb_batch_decode (word ids out), host wall clock"}
+    cb.close()
+    fst.close()
+    am.close()
+    pin_in.free()
+    return res
 
 
 def reference_outputs(cfg, g, n_utts=1):

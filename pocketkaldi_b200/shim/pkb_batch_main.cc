@@ -1,4 +1,5 @@
 // pocketkaldi_b200_batch <model-file> <list.scp | x.wav> [--threads N] [--batch-utts M] [--compact 0|1]
+//                        [--gpu-decode 0|1]
 //
 // Batch counterpart of the reference CLI (src/main.cc): same arguments, same
 // "<file>\t<hyp>\t<loglikelihood per frame>" lines in list order, but
@@ -8,7 +9,9 @@
 //   * fbank -> CMVN -> nnet run once per sub-batch on the GPU (pkb_batch_*), and
 //   * the reference's own Viterbi decoder (src/decoder.cc, unchanged) runs on a pool of host
 //     threads, each utterance starting as soon as ITS rows have reached host memory while the
-//     copy-out of later utterances is still in flight (pk_decodable_attach).
+//     copy-out of later utterances is still in flight (pk_decodable_attach), or
+//   * with --gpu-decode 1 the search itself runs on the GPU (pkb_batch_decode): the
+//     log-likelihoods never leave HBM and only word ids come back.
 // Model loading is the reference's pk_load compiled against the shim header.
 
 #include <math.h>
@@ -22,6 +25,7 @@
 #include <thread>
 #include <vector>
 
+#include "configuration.h"
 #include "decoder.h"
 #include "pkb200.h"
 #include "pocketkaldi.h"
@@ -78,10 +82,12 @@ int main(int argc, char **argv) {
   // compact rows (half the PCIe bytes, finished per look-up) are the default; --compact 0 moves
   // the FP32 matrix like pk_decodable_init does
   bool compact = true;
+  bool gpu_decode = false;
   for (int i = 3; i + 1 < argc; i += 2) {
     if (strcmp(argv[i], "--threads") == 0) n_threads = std::max(1, atoi(argv[i + 1]));
     else if (strcmp(argv[i], "--batch-utts") == 0) batch_utts = std::max(1, atoi(argv[i + 1]));
     else if (strcmp(argv[i], "--compact") == 0) compact = atoi(argv[i + 1]) != 0;
+    else if (strcmp(argv[i], "--gpu-decode") == 0) gpu_decode = atoi(argv[i + 1]) != 0;
   }
   const char *model_file = argv[1], *input_file = argv[2];
 
@@ -97,6 +103,18 @@ int main(int argc, char **argv) {
   pkb_ctx_t *ctx = pkb_shim_context();
   pkb_am_t *am = rec.am->handle();
   const int pdfs = rec.am->num_pdfs();
+
+  pkb_fst_t *gpu_fst = nullptr;
+  if (gpu_decode) {
+    pocketkaldi::Configuration conf;
+    pocketkaldi::Status st = conf.Read(model_file);
+    const std::string fst_path = st.ok() ? conf.GetPathOrElse("fst", "") : std::string();
+    if (fst_path.empty()) {
+      printf("pocketkaldi: Unable to find key 'fst' in %s\n", model_file);
+      return 1;
+    }
+    CHECK(pkb_fst_load(ctx, fst_path.c_str(), &gpu_fst));
+  }
 
   pkb_wavlist_t *list = nullptr;
   const size_t len = strlen(input_file);
@@ -120,6 +138,36 @@ int main(int argc, char **argv) {
     const int64_t frames = frame_off[n];
     pkb_batch_t *batch = nullptr;
     CHECK(pkb_batch_create(ctx, am, n, num_samples + first, rec.cmvn_global_stats->data, 0.1f, &batch));
+    if (gpu_decode) {
+      // the whole search on the device: only the word ids and one weight per utterance come back
+      void *pcm_g = nullptr;
+      CHECK(pkb_host_alloc(&pcm_g, std::max<int64_t>(samples, 1) * sizeof(int16_t)));
+      CHECK(pkb_wavlist_read_i16(list, first, n, static_cast<int16_t *>(pcm_g), n_threads));
+      CHECK(pkb_batch_set_pcm_i16(batch, static_cast<const int16_t *>(pcm_g)));
+      CHECK(pkb_batch_run(batch, PKB_STAGE_ALL | PKB_STAGE_NO_FEATS));
+      const int max_words = 1024;
+      std::vector<int32_t> words(static_cast<size_t>(n) * max_words), n_words(n);
+      std::vector<float> weight(n);
+      CHECK(pkb_batch_decode(batch, gpu_fst, 0.0f, 0, max_words, words.data(), n_words.data(), weight.data()));
+      for (int u = 0; u < n; ++u) {
+        if (num_samples[first + u] == 0) continue;
+        if (n_words[u] < 0) {
+          printf("pocketkaldi: %s: the GPU search ran out of its token capacity (code %d)\n",
+                 pkb_wavlist_path(list, first + u), n_words[u]);
+          return 1;
+        }
+        Result &r = results[first + u];
+        for (int i = 0; i < std::min(n_words[u], max_words); ++i) {
+          if (i != 0) r.hyp += ' ';
+          r.hyp += pk_symboltable_get(rec.symbol_table, words[static_cast<size_t>(u) * max_words + i]);
+        }
+        const int64_t T = frame_off[u + 1] - frame_off[u];
+        if (n_words[u] > 0 && T > 0) r.llpf = weight[u] / T;
+      }
+      pkb_host_free(pcm_g);
+      pkb_batch_destroy(batch);
+      continue;
+    }
     void *pcm = nullptr, *ll = nullptr, *off = nullptr;
     if (compact) CHECK(pkb_batch_set_compact(batch, 1));
     CHECK(pkb_host_alloc(&pcm, std::max<int64_t>(samples, 1) * sizeof(int16_t)));
@@ -169,6 +217,7 @@ int main(int argc, char **argv) {
   for (int i = 0; i < n_files; ++i)
     printf("%s\t%s\t%f\n", pkb_wavlist_path(list, i), results[i].hyp.c_str(), results[i].llpf);
   pkb_wavlist_destroy(list);
+  pkb_fst_destroy(gpu_fst);
   pk_destroy(&rec);
   return 0;
 }

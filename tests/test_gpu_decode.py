@@ -125,7 +125,8 @@ def test_batch_cli_prints_the_reference_lines(wavs, toy_conf, tmp_path):
     # compact rows (the default: half-size transfer finished in pk_decodable_loglikelihood) and
     # the FP32 matrix must both give the reference's words
     for extra in (["--threads", "3"], ["--threads", "2", "--batch-utts", "2"], ["--threads", "1", "--batch-utts", "1"],
-                  ["--threads", "3", "--compact", "0"], ["--threads", "2", "--batch-utts", "2", "--compact", "0"]):
+                  ["--threads", "3", "--compact", "0"], ["--threads", "2", "--batch-utts", "2", "--compact", "0"],
+                  ["--gpu-decode", "1"], ["--gpu-decode", "1", "--batch-utts", "2"]):
         res = run_cli(BATCH_CLI, toy_conf, scp, {"PKB_PRECISION": "bf16x3"}, extra)
         assert [r[0] for r in res] == ["en-us-%s.wav" % n for n in order]
         assert [r[1] for r in res] == [gold[n][0] for n in order], extra

@@ -141,7 +141,8 @@ def test_random_graphs_against_the_reference_cli(ctx, tmp_path, kind):
     g = synth_global_cmvn()
     conf = formats.write_model_dir(str(tmp_path), kind, layers, prior, 5, 5, tid2pdf, cmvn_stats=g, fst=fst,
                                    words=words)
-    lens = [16000, 24000, 8000, 32000, 400, 12345, 48000, 20000, 399, 28000]
+    # (an utterance shorter than one frame aborts the reference CLI: SURVEY appendix C)
+    lens = [16000, 24000, 8000, 32000, 400, 12345, 48000, 20000, 28000]
     pcms = [coloured(100 + u, n) for u, n in enumerate(lens)]
     paths = []
     for u, p in enumerate(pcms):

@@ -8,6 +8,7 @@ graph, N synthetic 10 s utterances and a .scp list into a scratch directory, the
   oracle/_ref/pocketkaldi_ref       (unmodified reference: one file at a time, CPU nnet)      [--ref]
   oracle/_ref/pocketkaldi_b200_cli  (reference main/decoder, acoustic half on the GPU per utterance)
   oracle/_ref/pocketkaldi_b200_batch (list ingestion + one GPU batch + decoder on host threads)
+  the same with --gpu-decode 1      (the Viterbi search on the GPU as well, pkb_batch_decode)
 and reports wall-clock seconds and how many hypotheses agree with the first CLI that ran.
 """
 
@@ -99,6 +100,8 @@ def main():
         extra = ("--threads", str(args.threads)) if args.threads > 0 else ()
         clis.append(("batch CLI (one GPU batch, decoder on host threads)",
                      os.path.join(ROOT, "oracle/_ref/pocketkaldi_b200_batch"), extra))
+        clis.append(("batch CLI --gpu-decode 1 (acoustic half + Viterbi on the GPU)",
+                     os.path.join(ROOT, "oracle/_ref/pocketkaldi_b200_batch"), extra + ("--gpu-decode", "1")))
         base = None
         audio = args.utts * args.seconds
         for name, cli, ex in clis:

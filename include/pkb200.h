@@ -287,6 +287,16 @@ int pkb_stream_max_frames(const pkb_stream_t *st);
 int pkb_stream_push_i16(pkb_stream_t *st, const int16_t *pcm, float *loglik_out,
                         int32_t *frames_out);
 int pkb_stream_flush(pkb_stream_t *st, float *loglik_out, int32_t *frames_out);
+/* From the second chunk of an utterance on every push has the same shapes; its launch sequence
+ * (tail copy, H2D, fbank, CMVN, nnet stages, D2H) is then captured once into a CUDA graph and
+ * replayed, provided the caller passes the same host buffers every time (other buffers are
+ * captured again). PKB_STREAM_GRAPH=0 in the environment keeps every push eager.
+ * Compact output of a stream (see pkb_batch_set_compact): h16_out [n_streams][max_frames][num_pdfs]
+ * half bits and off_out [n_streams][max_frames] offsets instead of the FP32 rows. */
+int pkb_stream_set_compact(pkb_stream_t *st, int on);
+int pkb_stream_push_compact_i16(pkb_stream_t *st, const int16_t *pcm, uint16_t *h16_out, float *off_out,
+                                int32_t *frames_out);
+int pkb_stream_flush_compact(pkb_stream_t *st, uint16_t *h16_out, float *off_out, int32_t *frames_out);
 
 /* ---- batched ingestion --------------------------------------
  * Host-side readers that feed the batch pipeline without the reference's detour through

@@ -105,6 +105,9 @@ _SIGNATURES = [
     ("pkb_stream_max_frames", C.c_int, [_VP]),
     ("pkb_stream_push_i16", C.c_int, [_VP, _VP, _VP, _VP]),
     ("pkb_stream_flush", C.c_int, [_VP, _VP, _VP]),
+    ("pkb_stream_set_compact", C.c_int, [_VP, C.c_int]),
+    ("pkb_stream_push_compact_i16", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    ("pkb_stream_flush_compact", C.c_int, [_VP, _VP, _VP, _VP]),
     ("pkb_wav_probe", C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("pkb_wav_read_i16", C.c_int, [C.c_char_p, _VP, C.c_int32, C.POINTER(C.c_int32)]),
     ("pkb_wav_read_f32", C.c_int, [C.c_char_p, _VP, C.c_int32, C.POINTER(C.c_int32)]),
@@ -764,3 +767,28 @@ class Stream:
         n = C.c_int32(0)
         _check(self.ctx.lib.pkb_stream_flush(self.h, out.ctypes.data, C.byref(n)))
         return out[:, :n.value]
+
+    def set_compact(self, on=True):
+        """Half-size output rows (see pkb_stream_set_compact): push_compact / flush_compact."""
+        _check(self.ctx.lib.pkb_stream_set_compact(self.h, 1 if on else 0))
+        if on and not hasattr(self, "out16"):
+            self.out16 = np.empty((self.n_streams, self.max_frames, self.P), np.uint16)
+            self.out_off = np.empty((self.n_streams, self.max_frames), np.float32)
+
+    def push_compact(self, pcm, out16=None, out_off=None):
+        """Returns views (h16 [n_streams][frames][P], off [n_streams][frames])."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        assert pcm.shape == (self.n_streams, self.chunk)
+        out16 = self.out16 if out16 is None else out16
+        out_off = self.out_off if out_off is None else out_off
+        n = C.c_int32(0)
+        _check(self.ctx.lib.pkb_stream_push_compact_i16(self.h, pcm.ctypes.data, out16.ctypes.data,
+                                                        out_off.ctypes.data, C.byref(n)))
+        return out16[:, :n.value], out_off[:, :n.value]
+
+    def flush_compact(self, out16=None, out_off=None):
+        out16 = self.out16 if out16 is None else out16
+        out_off = self.out_off if out_off is None else out_off
+        n = C.c_int32(0)
+        _check(self.ctx.lib.pkb_stream_flush_compact(self.h, out16.ctypes.data, out_off.ctypes.data, C.byref(n)))
+        return out16[:, :n.value], out_off[:, :n.value]

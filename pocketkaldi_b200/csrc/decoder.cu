@@ -29,7 +29,8 @@ namespace pkb {
 
 namespace {
 
-constexpr int kVitThreads = 128;
+constexpr int kVitThreads = 256;
+constexpr int kVitWarps = kVitThreads / 32;
 constexpr unsigned long long kEmptyVal = ~0ull;
 constexpr uint32_t kNoArc = 0xffffffffu;
 
@@ -136,6 +137,7 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
   w.log_ol = reinterpret_cast<int *>(wp);
 
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
 
   // Epsilon closure of table `c` (ProcessNonemitting, src/decoder.cc:203-237) under `cutoff`, then
   // the word back-pointers of every token of the frame. `p` is the previous frame's table.
@@ -159,11 +161,11 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
           const int slot = w.frontier[fb][i];
           const int state = tc.keys[slot] - 1;
           const float cost = cost_of(*reinterpret_cast<volatile unsigned long long *>(&tc.vals[slot]));
-          for (int a = fst.arc_begin[state]; a < fst.arc_begin[state + 1]; ++a) {
-            if (fst.arc_il[a] != 0) continue;
-            const double total = static_cast<double>(cost) + static_cast<double>(fst.arc_w[a]);
+          for (int a = __ldg(&fst.arc_begin[state]); a < __ldg(&fst.arc_begin[state + 1]); ++a) {
+            if (__ldg(&fst.arc_il[a]) != 0) continue;
+            const double total = static_cast<double>(cost) + static_cast<double>(__ldg(&fst.arc_w[a]));
             if (total > cutoff) continue;
-            const int s2 = tab_insert(tc, fst.arc_dst[a], mask, &s_ntok[c], max_tok);
+            const int s2 = tab_insert(tc, __ldg(&fst.arc_dst[a]), mask, &s_ntok[c], max_tok);
             if (s2 < 0) { s_err = 1; continue; }
             // InsertTok replaces only on a strictly lower cost (src/decoder.cc:127-134): CAS loop
             const unsigned long long nv = pack(static_cast<float>(total), static_cast<uint32_t>(a));
@@ -201,14 +203,14 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
         if (a == kNoArc) {
           pb = -1;  // the start token
         } else {
-          const int src = fst.arc_src[a];
-          if (fst.arc_il[a] != 0) {
+          const int src = __ldg(&fst.arc_src[a]);
+          if (__ldg(&fst.arc_il[a]) != 0) {
             pb = w.tab[p].bp[tab_find(w.tab[p], src, mask)];
           } else {
             pb = *reinterpret_cast<volatile int *>(&tc.bp[tab_find(tc, src, mask)]);
             if (pb == -2) { atomicAdd(&s_unres, 1); continue; }
           }
-          const int ol = fst.arc_ol[a];
+          const int ol = __ldg(&fst.arc_ol[a]);
           if (ol != 0) {
             const int r = atomicAdd(&s_log, 1);
             if (r >= max_log) { s_err = 2; pb = -1; }
@@ -275,38 +277,45 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
       if (tid == 0) s_min = ~0ull;
       __syncthreads();
       {
+        // one warp per token, lanes over its arcs: the loads of a token's arcs are independent
         unsigned long long m = ~0ull;
-        for (int i = tid; i < n_prev; i += kVitThreads) {
+        for (int i = warp; i < n_prev; i += kVitWarps) {
           const int slot = tp.list[i];
           const float cost = cost_of(tp.vals[slot]);
           if (cost > weight_cutoff) continue;
           const int state = tp.keys[slot] - 1;
-          for (int a = fst.arc_begin[state]; a < fst.arc_begin[state + 1]; ++a) {
-            const int il = fst.arc_il[a];
+          const int a1 = __ldg(&fst.arc_begin[state + 1]);
+          for (int a = __ldg(&fst.arc_begin[state]) + lane; a < a1; a += 32) {
+            const int il = __ldg(&fst.arc_il[a]);
             if (il == 0) continue;
-            const float ac = -ll[tid2pdf[il]];
-            const double total = static_cast<double>(cost) + static_cast<double>(fst.arc_w[a]) + static_cast<double>(ac);
+            const float ac = -__ldg(&ll[__ldg(&tid2pdf[il])]);
+            const double total = static_cast<double>(cost) + static_cast<double>(__ldg(&fst.arc_w[a])) +
+                                 static_cast<double>(ac);
             m = min(m, ord64(total));
           }
         }
-        atomicMin(&s_min, m);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) atomicMin(&s_min, m);
       }
       __syncthreads();
       if (s_min == ~0ull) { alive = false; break; }  // no arc left the beam: the reference has no tokens either
       const double next_cutoff = unord64(s_min) + static_cast<double>(beam);
       // ---- pass 2: create / improve the tokens of this frame
-      for (int i = tid; i < n_prev; i += kVitThreads) {
+      for (int i = warp; i < n_prev; i += kVitWarps) {
         const int slot = tp.list[i];
         const float cost = cost_of(tp.vals[slot]);
         if (cost > weight_cutoff) continue;
         const int state = tp.keys[slot] - 1;
-        for (int a = fst.arc_begin[state]; a < fst.arc_begin[state + 1]; ++a) {
-          const int il = fst.arc_il[a];
+        const int a1 = __ldg(&fst.arc_begin[state + 1]);
+        for (int a = __ldg(&fst.arc_begin[state]) + lane; a < a1; a += 32) {
+          const int il = __ldg(&fst.arc_il[a]);
           if (il == 0) continue;
-          const float ac = -ll[tid2pdf[il]];
-          const double total = static_cast<double>(cost) + static_cast<double>(fst.arc_w[a]) + static_cast<double>(ac);
+          const float ac = -__ldg(&ll[__ldg(&tid2pdf[il])]);
+          const double total = static_cast<double>(cost) + static_cast<double>(__ldg(&fst.arc_w[a])) +
+                               static_cast<double>(ac);
           if (total > next_cutoff) continue;
-          const int s2 = tab_insert(tc, fst.arc_dst[a], mask, &s_ntok[cur], max_tok);
+          const int s2 = tab_insert(tc, __ldg(&fst.arc_dst[a]), mask, &s_ntok[cur], max_tok);
           if (s2 < 0) { s_err = 1; continue; }
           atomicMin(&tc.vals[s2], pack(static_cast<float>(total), static_cast<uint32_t>(a)));
         }
@@ -471,7 +480,7 @@ int launch_viterbi(Ctx *c, const pkb_fst *fst, const ViterbiConfig &cfg, const f
                             2 * sizeof(int) * static_cast<size_t>(cfg.max_log);
   const size_t stride = (stride_raw + 255) & ~static_cast<size_t>(255);
   // persistent blocks: a few per SM, each walking its share of the utterances with one workspace
-  const int grid = std::min(n_utts, c->sm_count * 4);
+  const int grid = std::min(n_utts, c->sm_count * 8);
   const size_t bytes = stride * grid;
   PKB_TRY(work->ensure(bytes));
   // invariant the kernel relies on (and restores per utterance): keys 0, values empty, queue flags 0

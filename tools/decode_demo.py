@@ -100,6 +100,8 @@ def main():
         extra = ("--threads", str(args.threads)) if args.threads > 0 else ()
         clis.append(("batch CLI (one GPU batch, decoder on host threads)",
                      os.path.join(ROOT, "oracle/_ref/pocketkaldi_b200_batch"), extra))
+        clis.append(("batch CLI --compact 0 (FP32 rows to the host decoder threads)",
+                     os.path.join(ROOT, "oracle/_ref/pocketkaldi_b200_batch"), extra + ("--compact", "0")))
         clis.append(("batch CLI --gpu-decode 1 (acoustic half + Viterbi on the GPU)",
                      os.path.join(ROOT, "oracle/_ref/pocketkaldi_b200_batch"), extra + ("--gpu-decode", "1")))
         base = None

@@ -114,14 +114,18 @@ __global__ void __launch_bounds__(kVitThreads)
 viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, int max_words,
                const float *__restrict__ loglik, int num_pdfs, const int64_t *__restrict__ row_off,
                const int32_t *__restrict__ num_frames, int n_utts, const int32_t *__restrict__ tid2pdf,
-               char *work_base, size_t work_stride, int32_t *__restrict__ words_out,
+               char *work_base, size_t work_stride, int tables_in_smem, int32_t *__restrict__ words_out,
                int32_t *__restrict__ n_words_out, float *__restrict__ weight_out) {
   __shared__ int s_ntok[2], s_nfront[2], s_log, s_err, s_unres;
   __shared__ unsigned long long s_min;
 
-  // carve this block's workspace
+  // carve this block's workspace. Small graphs (every state fits the token capacity chosen by the
+  // launcher) keep the two token tables, the lists and the queue in shared memory: the per-frame
+  // chain of dependent look-ups and atomics then never leaves the SM. The word records stay global.
+  extern __shared__ __align__(16) char s_tab[];
   const uint32_t H = mask + 1;
-  char *wp = work_base + static_cast<size_t>(blockIdx.x) * work_stride;
+  char *gp = work_base + static_cast<size_t>(blockIdx.x) * work_stride;
+  char *wp = tables_in_smem ? s_tab : gp;
   Work w;
   for (int i = 0; i < 2; ++i) {
     w.tab[i].vals = reinterpret_cast<unsigned long long *>(wp); wp += sizeof(unsigned long long) * H;
@@ -133,10 +137,22 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
     w.frontier[i] = reinterpret_cast<int *>(wp); wp += sizeof(int) * max_tok;
   }
   w.inq = reinterpret_cast<int *>(wp); wp += sizeof(int) * H;
+  if (tables_in_smem) wp = gp;  // the global workspace then holds the word records only
   w.log_prev = reinterpret_cast<int *>(wp); wp += sizeof(int) * max_log;
   w.log_ol = reinterpret_cast<int *>(wp);
 
   const int tid = threadIdx.x;
+  if (tables_in_smem) {
+    // the invariant the global workspace gets from the launcher's memset
+    for (uint32_t i = tid; i < H; i += kVitThreads) {
+      for (int k = 0; k < 2; ++k) {
+        w.tab[k].keys[i] = 0;
+        w.tab[k].vals[i] = kEmptyVal;
+      }
+      w.inq[i] = 0;
+    }
+    __syncthreads();
+  }
   const int warp = tid >> 5, lane = tid & 31;
 
   // Epsilon closure of table `c` (ProcessNonemitting, src/decoder.cc:203-237) under `cutoff`, then
@@ -473,23 +489,32 @@ int launch_viterbi(Ctx *c, const pkb_fst *fst, const ViterbiConfig &cfg, const f
   if (n_utts == 0) return PKB_OK;
   PKB_REQUIRE(cfg.max_tokens >= 16 && cfg.max_log >= 16 && cfg.max_words >= 1 && cfg.beam > 0.0f,
               "pkb_batch_decode: bad configuration");
+  // a graph with at most 512 states can never hold more tokens than states: its tables go to
+  // shared memory (capacity = the state count), whatever max_tokens says
+  const bool small = fst->num_states <= 512;
+  const int max_tok = small ? std::max(16, fst->num_states) : cfg.max_tokens;
   uint32_t H = 64;
-  while (H < 2u * static_cast<uint32_t>(cfg.max_tokens)) H <<= 1;
-  const size_t stride_raw = 2 * sizeof(unsigned long long) * H +
-                            2 * (2 * sizeof(int) * H + 2 * sizeof(int) * cfg.max_tokens) + sizeof(int) * H +
-                            2 * sizeof(int) * static_cast<size_t>(cfg.max_log);
+  while (H < 2u * static_cast<uint32_t>(max_tok)) H <<= 1;
+  const size_t table_bytes = 2 * sizeof(unsigned long long) * H +
+                             2 * (2 * sizeof(int) * H + 2 * sizeof(int) * max_tok) + sizeof(int) * H;
+  const size_t log_bytes = 2 * sizeof(int) * static_cast<size_t>(cfg.max_log);
+  const size_t stride_raw = (small ? 0 : table_bytes) + log_bytes;
   const size_t stride = (stride_raw + 255) & ~static_cast<size_t>(255);
   // persistent blocks: a few per SM, each walking its share of the utterances with one workspace
   const int grid = std::min(n_utts, c->sm_count * 8);
   const size_t bytes = stride * grid;
   PKB_TRY(work->ensure(bytes));
-  // invariant the kernel relies on (and restores per utterance): keys 0, values empty, queue flags 0
-  PKB_CUDA(cudaMemsetAsync(work->p, 0, bytes, c->stream));
-  {
+  if (!small) {
+    // invariant the kernel relies on (and restores per utterance): keys 0, values empty, queue flags 0
+    PKB_CUDA(cudaMemsetAsync(work->p, 0, bytes, c->stream));
     LaunchScope scope(c, PKB_KERNEL_MISC);
     viterbi_init_kernel<<<dim3(4, grid), 256, 0, c->stream>>>(work->as<char>(), stride, 2 * H);
     PKB_CUDA(cudaGetLastError());
   }
+  const size_t dyn_smem = small ? table_bytes : 0;
+  if (dyn_smem > 48 * 1024)
+    PKB_CUDA(cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(dyn_smem)));
   FstDev fd;
   fd.num_states = fst->num_states;
   fd.start = fst->start;
@@ -502,10 +527,10 @@ int launch_viterbi(Ctx *c, const pkb_fst *fst, const ViterbiConfig &cfg, const f
   fd.arc_ol = fst->d_arc_ol;
   fd.arc_w = fst->d_arc_w;
   LaunchScope scope(c, PKB_KERNEL_MISC);
-  viterbi_kernel<<<grid, kVitThreads, 0, c->stream>>>(fd, cfg.beam, cfg.max_tokens, H - 1, cfg.max_log,
-                                                      cfg.max_words, d_loglik, num_pdfs, d_row_off,
-                                                      d_num_frames, n_utts, d_tid2pdf, work->as<char>(),
-                                                      stride, d_words, d_n_words, d_weight);
+  viterbi_kernel<<<grid, kVitThreads, dyn_smem, c->stream>>>(fd, cfg.beam, max_tok, H - 1, cfg.max_log,
+                                                             cfg.max_words, d_loglik, num_pdfs, d_row_off,
+                                                             d_num_frames, n_utts, d_tid2pdf, work->as<char>(),
+                                                             stride, small ? 1 : 0, d_words, d_n_words, d_weight);
   PKB_CUDA(cudaGetLastError());
   return PKB_OK;
 }

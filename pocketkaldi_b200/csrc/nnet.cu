@@ -88,6 +88,27 @@ __global__ void pack_plain_kernel(const float *__restrict__ in, int64_t rows, in
   if (lo) lo[g] = operand_bits(v - operand_value(h, fp16), fp16);
 }
 
+// FP16C8 weight planes from the FP32 matrix (one thread per element of the padded planes).
+__global__ void pack_c8_kernel(const float *__restrict__ W, int out_dim, int in_dim, int n_pad, int k_pad,
+                               int k_pad8, float sg, __nv_bfloat16 *__restrict__ w16, uint8_t *__restrict__ h8,
+                               uint8_t *__restrict__ l8) {
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int o = static_cast<int>(g / k_pad8), k = static_cast<int>(g % k_pad8);
+  if (o >= n_pad) return;
+  float w = 0.0f;
+  if (o < out_dim && k < in_dim) w = W[static_cast<int64_t>(o) * in_dim + k] * sg;
+  const __half h = __float2half_rn(w);
+  const float wf = __half2float(h);
+  if (k < k_pad) {
+    const __half_raw hr = static_cast<__half_raw>(h);
+    __nv_bfloat16_raw br;
+    br.x = hr.x;
+    w16[static_cast<int64_t>(o) * k_pad + k] = __nv_bfloat16(br);
+  }
+  h8[g] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(wf * 16.0f, __NV_SATFINITE, __NV_E4M3));
+  l8[g] = static_cast<uint8_t>(__nv_cvt_float_to_fp8((w - wf) * 8192.0f, __NV_SATFINITE, __NV_E4M3));
+}
+
 // ---------------------------------------------------------------- weight packing
 // W[out][in] float -> BF16 planes [n_pad][k_pad]; column c of the source goes to
 // column remap(c) (identity, or the padded splice layout).
@@ -144,10 +165,6 @@ int pack_stage(Ctx *c, Stage *st, const float *W, const float *b, int out_dim, i
   return PKB_OK;
 }
 
-inline uint8_t to_e4m3(float v) {
-  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3));
-}
-
 // Operand mode 3 (FP16C8) planes of W[out][in]: W16 = fp16(W * 2^g) with max |W * 2^g| in [1, 2),
 // W_hi8 = e4m3(W16 * 2^4), W_lo8 = e4m3((W * 2^g - W16) * 2^13); see gemm_sm100.cu.
 int pack_stage_c8(Ctx *c, Stage *st, const float *W, const float *b, int out_dim, int in_dim) {
@@ -167,29 +184,28 @@ int pack_stage_c8(Ctx *c, Stage *st, const float *W, const float *b, int out_dim
   st->w_exp = wmax > 0.0f ? 1 - e : 0; // W * 2^g has its maximum in [1, 2)
   const float sg = ldexpf(1.0f, st->w_exp);
   const size_t e16 = static_cast<size_t>(st->n_pad) * st->k_pad, e8 = static_cast<size_t>(st->n_pad) * st->k_pad8;
-  std::vector<__nv_bfloat16> hi(e16, operand_bits(0.0f, 1));
-  std::vector<uint8_t> h8(e8, 0), l8(e8, 0);
-  for (int o = 0; o < out_dim; ++o) {
-    const float *src = W + static_cast<size_t>(o) * in_dim;
-    for (int k = 0; k < in_dim; ++k) {
-      const float w = src[k] * sg;
-      const __nv_bfloat16 h = operand_bits(w, 1);
-      const float w16 = operand_value(h, 1);
-      hi[static_cast<size_t>(o) * st->k_pad + k] = h;
-      h8[static_cast<size_t>(o) * st->k_pad8 + k] = to_e4m3(w16 * 16.0f);
-      l8[static_cast<size_t>(o) * st->k_pad8 + k] = to_e4m3((w - w16) * 8192.0f);
-    }
-  }
   std::vector<float> bias(st->n_pad, 0.0f);
   memcpy(bias.data(), b, sizeof(float) * out_dim);
   PKB_TRY(st->w_hi.ensure(e16 * 2));
-  PKB_CUDA(cudaMemcpy(st->w_hi.p, hi.data(), e16 * 2, cudaMemcpyHostToDevice));
   PKB_TRY(st->w8_hi.ensure(e8));
-  PKB_CUDA(cudaMemcpy(st->w8_hi.p, h8.data(), e8, cudaMemcpyHostToDevice));
   PKB_TRY(st->w8_lo.ensure(e8));
-  PKB_CUDA(cudaMemcpy(st->w8_lo.p, l8.data(), e8, cudaMemcpyHostToDevice));
   PKB_TRY(st->bias.ensure(sizeof(float) * st->n_pad));
   PKB_CUDA(cudaMemcpy(st->bias.p, bias.data(), sizeof(float) * st->n_pad, cudaMemcpyHostToDevice));
+  {
+    // the planes are rounded on the device: 2 x 8.8 M scalar FP8 conversions on the host would
+    // dominate the model load of the config-3 net
+    DevBuf tmp;
+    const size_t wbytes = static_cast<size_t>(out_dim) * in_dim * sizeof(float);
+    PKB_TRY(tmp.ensure(wbytes));
+    PKB_CUDA(cudaMemcpy(tmp.p, W, wbytes, cudaMemcpyHostToDevice));
+    const int64_t threads = static_cast<int64_t>(e8);
+    pack_c8_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(
+        tmp.as<float>(), out_dim, in_dim, st->n_pad, st->k_pad, st->k_pad8, sg, st->w_hi.as<__nv_bfloat16>(),
+        st->w8_hi.as<uint8_t>(), st->w8_lo.as<uint8_t>());
+    PKB_CUDA(cudaGetLastError());
+    PKB_CUDA(cudaStreamSynchronize(c->stream));
+    tmp.release();
+  }
   const uint64_t p16 = static_cast<uint64_t>(st->k_pad) * 2, p8 = static_cast<uint64_t>(st->k_pad8);
   PKB_TRY(make_tensor_map(&st->tm_w_hi, st->w_hi.p, st->k_pad, st->n_pad, p16, st->block_n));
   PKB_TRY(make_tensor_map(&st->tm_w_hi_half, st->w_hi.p, st->k_pad, st->n_pad, p16, st->block_n / 2));

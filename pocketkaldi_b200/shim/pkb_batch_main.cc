@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <atomic>
@@ -34,6 +35,21 @@
 using pocketkaldi::Decoder;
 
 namespace {
+
+// PKB_CLI_TIMING=1: wall-clock milestones on stderr
+double now_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+void milestone(const char *what) {
+  static const bool on = getenv("PKB_CLI_TIMING") != nullptr;
+  static double t0 = now_s(), last = t0;
+  if (!on) return;
+  const double t = now_s();
+  fprintf(stderr, "[pkb batch] %-28s +%.3f s (%.3f s)\n", what, t - last, t - t0);
+  last = t;
+}
 
 void die(const char *what) {
   printf("pocketkaldi: %s: %s\n", what, pkb_last_error());
@@ -91,6 +107,7 @@ int main(int argc, char **argv) {
   }
   const char *model_file = argv[1], *input_file = argv[2];
 
+  milestone("start");
   pk_t rec;
   pk_status_t status;
   pk_status_init(&status);
@@ -100,6 +117,7 @@ int main(int argc, char **argv) {
     printf("pocketkaldi: %s\n", status.message);
     return 1;
   }
+  milestone("pk_load");
   pkb_ctx_t *ctx = pkb_shim_context();
   pkb_am_t *am = rec.am->handle();
   const int pdfs = rec.am->num_pdfs();
@@ -123,6 +141,7 @@ int main(int argc, char **argv) {
   } else {
     CHECK(pkb_scp_open(input_file, &list));
   }
+  milestone("fst + list headers");
   const int n_files = pkb_wavlist_size(list);
   const int32_t *num_samples = pkb_wavlist_num_samples(list);
 
@@ -145,10 +164,12 @@ int main(int argc, char **argv) {
       CHECK(pkb_wavlist_read_i16(list, first, n, static_cast<int16_t *>(pcm_g), n_threads));
       CHECK(pkb_batch_set_pcm_i16(batch, static_cast<const int16_t *>(pcm_g)));
       CHECK(pkb_batch_run(batch, PKB_STAGE_ALL | PKB_STAGE_NO_FEATS));
+      milestone("read wavs + queue batch");
       const int max_words = 1024;
       std::vector<int32_t> words(static_cast<size_t>(n) * max_words), n_words(n);
       std::vector<float> weight(n);
       CHECK(pkb_batch_decode(batch, gpu_fst, 0.0f, 0, max_words, words.data(), n_words.data(), weight.data()));
+      milestone("acoustic + GPU Viterbi");
       for (int u = 0; u < n; ++u) {
         if (num_samples[first + u] == 0) continue;
         if (n_words[u] < 0) {
@@ -206,7 +227,9 @@ int main(int argc, char **argv) {
     };
     std::vector<std::thread> pool;
     for (int t = 0; t < std::min(n_threads, n); ++t) pool.emplace_back(work);
+    milestone("read wavs + queue batch");
     for (auto &t : pool) t.join();
+    milestone("host decoder threads");
     CHECK(pkb_sync(ctx));
     for (pkb_event_t *e : ready) pkb_event_destroy(e);
     pkb_host_free(pcm);
@@ -214,6 +237,7 @@ int main(int argc, char **argv) {
     pkb_host_free(off);
     pkb_batch_destroy(batch);
   }
+  milestone("batches done");
   for (int i = 0; i < n_files; ++i)
     printf("%s\t%s\t%f\n", pkb_wavlist_path(list, i), results[i].hyp.c_str(), results[i].llpf);
   pkb_wavlist_destroy(list);

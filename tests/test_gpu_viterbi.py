@@ -119,22 +119,25 @@ def eps_graph(n_words, n_hmm, num_pdfs):
     return (2 + n_words + n_words * n_hmm, 0, finals, arcs), tid2pdf
 
 
-@pytest.mark.parametrize("kind", ["loop", "eps"])
+@pytest.mark.parametrize("kind", ["loop", "eps", "loop_big"])
 def test_random_graphs_against_the_reference_cli(ctx, tmp_path, kind):
+    # "loop" / "eps": small graphs, token tables in shared memory; "loop_big": 541 states, the
+    # tables live in the global workspace
     if not os.path.exists(REF_CLI):
         pytest.skip("oracle/_ref/pocketkaldi_ref not built")
-    rng = np.random.default_rng(1 if kind == "loop" else 2)
-    P = 96
+    rng = np.random.default_rng({"loop": 1, "eps": 2, "loop_big": 3}[kind])
+    P = 600 if kind == "loop_big" else 96
     layers = formats.make_dnn(rng, 440, 96, 2, P)
     # make the acoustic scores decisive enough that a 1e-4 difference between the CPU and the GPU
     # nnet cannot flip a path, but keep several words alive in the beam
     layers[-2] = ("linear", (layers[-2][1] * 3.0).astype(np.float32), layers[-2][2])
     prior = rng.uniform(0.5, 1.5, P).astype(np.float32)
     prior /= prior.sum()
-    if kind == "loop":
+    if kind.startswith("loop"):
         import tools.decode_demo as demo
-        fst, tid2pdf = demo.word_loop_graph(12, 3, P)
-        words = ["<eps>"] + ["w%02d" % i for i in range(12)]
+        nw = 180 if kind == "loop_big" else 12
+        fst, tid2pdf = demo.word_loop_graph(nw, 3, P)
+        words = ["<eps>"] + ["w%03d" % i for i in range(nw)]
     else:
         fst, tid2pdf = eps_graph(10, 3, P)
         words = ["<eps>"] + ["w%02d" % i for i in range(10)] + ["</w>"]
@@ -162,16 +165,16 @@ def test_random_graphs_against_the_reference_cli(ctx, tmp_path, kind):
 
 def test_capacity_overflow_is_reported_not_silent(ctx, tmp_path):
     rng = np.random.default_rng(3)
-    P = 64
+    import tools.decode_demo as demo
+    P = 640
     layers = formats.make_dnn(rng, 440, 32, 1, P)
     prior = np.full(P, 1.0 / P, np.float32)
-    import tools.decode_demo as demo
-    fst, tid2pdf = demo.word_loop_graph(20, 3, P)   # 61 states
+    fst, tid2pdf = demo.word_loop_graph(200, 3, P)   # 601 states: tables in the global workspace
     g = synth_global_cmvn()
     conf = formats.write_model_dir(str(tmp_path), "ovf", layers, prior, 5, 5, tid2pdf, cmvn_stats=g, fst=fst,
-                                   words=["<eps>"] + ["w%02d" % i for i in range(20)])
-    pcms = [synth_pcm(5, [0], 16000)[0]]
-    hyps, _, _ = gpu_decode(ctx, conf, pcms, g, max_tokens=16)
-    assert hyps[0] is None                      # 61 live states do not fit 16 tokens: flagged
-    hyps, _, _ = gpu_decode(ctx, conf, pcms, g, max_tokens=128)
-    assert hyps[0] is not None and len(hyps[0]) > 0   # and the workspace is clean afterwards
+                                   words=["<eps>"] + ["w%03d" % i for i in range(200)])
+    pcms = [synth_pcm(5, [0], 16000)[0], synth_pcm(5, [1], 16000)[0]]
+    hyps, _, _ = gpu_decode(ctx, conf, pcms, g, max_tokens=64)
+    assert hyps[0] is None and hyps[1] is None  # hundreds of live states do not fit 64 tokens: flagged
+    hyps, _, _ = gpu_decode(ctx, conf, pcms, g, max_tokens=1024)
+    assert all(h is not None and len(h) > 0 for h in hyps)   # and the workspace is clean afterwards

@@ -58,8 +58,9 @@ def run(cli, conf, scp, env, extra=()):
     e = dict(os.environ)
     e.update(env)
     t0 = time.perf_counter()
-    out = subprocess.run([cli, conf, scp] + list(extra), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                         env=e, check=True).stdout.decode()
+    r = subprocess.run([cli, conf, scp] + list(extra), stdout=subprocess.PIPE,
+                       stderr=None if os.environ.get("PKB_CLI_TIMING") else subprocess.DEVNULL, env=e, check=True)
+    out = r.stdout.decode()
     dt = time.perf_counter() - t0
     hyps = [line.split("\t")[1].strip() for line in out.strip().splitlines()]
     return dt, hyps

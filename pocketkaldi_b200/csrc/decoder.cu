@@ -30,7 +30,8 @@ namespace pkb {
 namespace {
 
 constexpr int kVitThreads = 256;
-constexpr int kVitWarps = kVitThreads / 32;
+constexpr int kVitGroup = 8;                       // lanes that share one token's arcs
+constexpr int kVitGroups = kVitThreads / kVitGroup;
 constexpr unsigned long long kEmptyVal = ~0ull;
 constexpr uint32_t kNoArc = 0xffffffffu;
 
@@ -82,18 +83,19 @@ __device__ __forceinline__ uint32_t hash_state(int s) { return static_cast<uint3
 // slot of `state`, or -1
 __device__ __forceinline__ int tab_find(const Tab &t, int state, uint32_t mask) {
   uint32_t s = hash_state(state) & mask;
-  for (;;) {
+  for (uint32_t n = 0; n <= mask; ++n) {
     const int k = t.keys[s];
     if (k == state + 1) return static_cast<int>(s);
     if (k == 0) return -1;
     s = (s + 1) & mask;
   }
+  return -1;
 }
 
 // slot of `state`, claiming an empty one (and appending it to the list) when it is new; -1 on overflow
 __device__ __forceinline__ int tab_insert(const Tab &t, int state, uint32_t mask, int *n_tok, int max_tok) {
   uint32_t s = hash_state(state) & mask;
-  for (;;) {
+  for (uint32_t n = 0; n <= mask; ++n) {  // bounded: a full table (capacity overflow) must not spin
     int k = *reinterpret_cast<volatile int *>(&t.keys[s]);
     if (k == 0) {
       k = atomicCAS(&t.keys[s], 0, state + 1);
@@ -108,13 +110,15 @@ __device__ __forceinline__ int tab_insert(const Tab &t, int state, uint32_t mask
     if (k == state + 1) return static_cast<int>(s);
     s = (s + 1) & mask;
   }
+  return -1;
 }
 
 __global__ void __launch_bounds__(kVitThreads)
 viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, int max_words,
                const float *__restrict__ loglik, int num_pdfs, const int64_t *__restrict__ row_off,
                const int32_t *__restrict__ num_frames, int n_utts, const int32_t *__restrict__ tid2pdf,
-               char *work_base, size_t work_stride, int tables_in_smem, int32_t *__restrict__ words_out,
+               char *work_base, size_t work_stride, int tables_in_smem, int rows_in_smem,
+               int32_t *__restrict__ words_out,
                int32_t *__restrict__ n_words_out, float *__restrict__ weight_out) {
   __shared__ int s_ntok[2], s_nfront[2], s_log, s_err, s_unres;
   __shared__ unsigned long long s_min;
@@ -137,6 +141,15 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
     w.frontier[i] = reinterpret_cast<int *>(wp); wp += sizeof(int) * max_tok;
   }
   w.inq = reinterpret_cast<int *>(wp); wp += sizeof(int) * H;
+  // two log-likelihood rows (this frame's and the next one's, fetched with cp.async while this
+  // frame is searched) follow the tables in shared memory when they fit
+  float *s_row[2] = {nullptr, nullptr};
+  if (rows_in_smem) {
+    char *rp = tables_in_smem ? wp : s_tab;
+    rp = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(rp) + 15) & ~static_cast<uintptr_t>(15));
+    s_row[0] = reinterpret_cast<float *>(rp);
+    s_row[1] = s_row[0] + ((num_pdfs + 3) & ~3);
+  }
   if (tables_in_smem) wp = gp;  // the global workspace then holds the word records only
   w.log_prev = reinterpret_cast<int *>(wp); wp += sizeof(int) * max_log;
   w.log_ol = reinterpret_cast<int *>(wp);
@@ -153,7 +166,7 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
     }
     __syncthreads();
   }
-  const int warp = tid >> 5, lane = tid & 31;
+  const int grp = tid / kVitGroup, gl = tid % kVitGroup;
 
   // Epsilon closure of table `c` (ProcessNonemitting, src/decoder.cc:203-237) under `cutoff`, then
   // the word back-pointers of every token of the frame. `p` is the previous frame's table.
@@ -221,9 +234,11 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
         } else {
           const int src = __ldg(&fst.arc_src[a]);
           if (__ldg(&fst.arc_il[a]) != 0) {
-            pb = w.tab[p].bp[tab_find(w.tab[p], src, mask)];
+            const int ps = tab_find(w.tab[p], src, mask);
+            pb = ps >= 0 ? w.tab[p].bp[ps] : -1;
           } else {
-            pb = *reinterpret_cast<volatile int *>(&tc.bp[tab_find(tc, src, mask)]);
+            const int cs = tab_find(tc, src, mask);
+            pb = cs >= 0 ? *reinterpret_cast<volatile int *>(&tc.bp[cs]) : -1;
             if (pb == -2) { atomicAdd(&s_unres, 1); continue; }
           }
           const int ol = __ldg(&fst.arc_ol[a]);
@@ -270,6 +285,20 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
     __syncthreads();
     close_and_resolve(0, 1, INFINITY);
 
+    // 16-byte chunks of one row (rows_in_smem requires num_pdfs % 4 == 0: every row is 16-byte aligned)
+    auto fetch_row = [&](int f) {
+      if (f < T) {
+        const float *src = ll0 + static_cast<int64_t>(f) * num_pdfs;
+        float *dst = s_row[f & 1];
+        for (int i = tid * 4; i < num_pdfs; i += kVitThreads * 4)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                           static_cast<uint32_t>(__cvta_generic_to_shared(dst + i))),
+                       "l"(src + i)
+                       : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (rows_in_smem) fetch_row(0);
     bool alive = true;
     for (int f = 0; f < T && alive && !s_err; ++f) {
       const int prev = cur;
@@ -277,6 +306,11 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
       const Tab &tp = w.tab[prev], &tc = w.tab[cur];
       const int n_prev = s_ntok[prev];
       const float *ll = ll0 + static_cast<int64_t>(f) * num_pdfs;
+      if (rows_in_smem) {
+        fetch_row(f + 1);  // into the buffer the previous frame is done with (block-wide barriers since)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        ll = s_row[f & 1];
+      }
       // ---- GetCutoff (src/decoder.cc:141-200) below kBeamSize tokens: best cost + beam
       if (tid == 0) s_min = ~0ull;
       __syncthreads();
@@ -293,18 +327,19 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
       if (tid == 0) s_min = ~0ull;
       __syncthreads();
       {
-        // one warp per token, lanes over its arcs: the loads of a token's arcs are independent
+        // eight lanes per token, lanes over its arcs: 32 tokens of the block are in flight at once
         unsigned long long m = ~0ull;
-        for (int i = warp; i < n_prev; i += kVitWarps) {
+        for (int i = grp; i < n_prev; i += kVitGroups) {
           const int slot = tp.list[i];
           const float cost = cost_of(tp.vals[slot]);
           if (cost > weight_cutoff) continue;
           const int state = tp.keys[slot] - 1;
           const int a1 = __ldg(&fst.arc_begin[state + 1]);
-          for (int a = __ldg(&fst.arc_begin[state]) + lane; a < a1; a += 32) {
+          for (int a = __ldg(&fst.arc_begin[state]) + gl; a < a1; a += kVitGroup) {
             const int il = __ldg(&fst.arc_il[a]);
             if (il == 0) continue;
-            const float ac = -__ldg(&ll[__ldg(&tid2pdf[il])]);
+            const int pdf = __ldg(&tid2pdf[il]);
+            const float ac = -(rows_in_smem ? ll[pdf] : __ldg(&ll[pdf]));
             const double total = static_cast<double>(cost) + static_cast<double>(__ldg(&fst.arc_w[a])) +
                                  static_cast<double>(ac);
             m = min(m, ord64(total));
@@ -312,22 +347,23 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
         }
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) atomicMin(&s_min, m);
+        if ((tid & 31) == 0) atomicMin(&s_min, m);
       }
       __syncthreads();
       if (s_min == ~0ull) { alive = false; break; }  // no arc left the beam: the reference has no tokens either
       const double next_cutoff = unord64(s_min) + static_cast<double>(beam);
       // ---- pass 2: create / improve the tokens of this frame
-      for (int i = warp; i < n_prev; i += kVitWarps) {
+      for (int i = grp; i < n_prev; i += kVitGroups) {
         const int slot = tp.list[i];
         const float cost = cost_of(tp.vals[slot]);
         if (cost > weight_cutoff) continue;
         const int state = tp.keys[slot] - 1;
         const int a1 = __ldg(&fst.arc_begin[state + 1]);
-        for (int a = __ldg(&fst.arc_begin[state]) + lane; a < a1; a += 32) {
+        for (int a = __ldg(&fst.arc_begin[state]) + gl; a < a1; a += kVitGroup) {
           const int il = __ldg(&fst.arc_il[a]);
           if (il == 0) continue;
-          const float ac = -__ldg(&ll[__ldg(&tid2pdf[il])]);
+          const int pdf = __ldg(&tid2pdf[il]);
+          const float ac = -(rows_in_smem ? ll[pdf] : __ldg(&ll[pdf]));
           const double total = static_cast<double>(cost) + static_cast<double>(__ldg(&fst.arc_w[a])) +
                                static_cast<double>(ac);
           if (total > next_cutoff) continue;
@@ -342,6 +378,7 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
       clear_tab(prev);
     }
 
+    if (rows_in_smem) asm volatile("cp.async.wait_group 0;" ::: "memory");
     // ---- BestPath (src/decoder.cc:300-339)
     if (tid == 0) s_min = ~0ull;
     __syncthreads();
@@ -511,7 +548,9 @@ int launch_viterbi(Ctx *c, const pkb_fst *fst, const ViterbiConfig &cfg, const f
     viterbi_init_kernel<<<dim3(4, grid), 256, 0, c->stream>>>(work->as<char>(), stride, 2 * H);
     PKB_CUDA(cudaGetLastError());
   }
-  const size_t dyn_smem = small ? table_bytes : 0;
+  const size_t row_bytes = 2 * sizeof(float) * static_cast<size_t>((num_pdfs + 3) & ~3) + 16;
+  const bool rows = (num_pdfs % 4) == 0 && (small ? table_bytes : 0) + row_bytes <= 96 * 1024;
+  const size_t dyn_smem = (small ? table_bytes : 0) + (rows ? row_bytes : 0);
   if (dyn_smem > 48 * 1024)
     PKB_CUDA(cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(dyn_smem)));
@@ -530,7 +569,8 @@ int launch_viterbi(Ctx *c, const pkb_fst *fst, const ViterbiConfig &cfg, const f
   viterbi_kernel<<<grid, kVitThreads, dyn_smem, c->stream>>>(fd, cfg.beam, max_tok, H - 1, cfg.max_log,
                                                              cfg.max_words, d_loglik, num_pdfs, d_row_off,
                                                              d_num_frames, n_utts, d_tid2pdf, work->as<char>(),
-                                                             stride, small ? 1 : 0, d_words, d_n_words, d_weight);
+                                                             stride, small ? 1 : 0, rows ? 1 : 0, d_words, d_n_words,
+                                                             d_weight);
   PKB_CUDA(cudaGetLastError());
   return PKB_OK;
 }

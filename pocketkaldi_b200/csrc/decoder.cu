@@ -20,6 +20,7 @@
 // equal float costs are broken by arc index instead of by list order.
 
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -30,8 +31,8 @@ namespace pkb {
 namespace {
 
 constexpr int kVitThreads = 256;
-constexpr int kVitGroup = 8;                       // lanes that share one token's arcs
-constexpr int kVitGroups = kVitThreads / kVitGroup;
+// kVitGroup lanes share one token's arcs: 8 for graphs with a few arcs per state, a whole warp for
+// dense ones (the launcher picks by the average out-degree)
 constexpr unsigned long long kEmptyVal = ~0ull;
 constexpr uint32_t kNoArc = 0xffffffffu;
 
@@ -113,12 +114,12 @@ __device__ __forceinline__ int tab_insert(const Tab &t, int state, uint32_t mask
   return -1;
 }
 
+template <int kVitGroup>
 __global__ void __launch_bounds__(kVitThreads)
 viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, int max_words,
                const float *__restrict__ loglik, int num_pdfs, const int64_t *__restrict__ row_off,
                const int32_t *__restrict__ num_frames, int n_utts, const int32_t *__restrict__ tid2pdf,
-               char *work_base, size_t work_stride, int tables_in_smem, int rows_in_smem,
-               int32_t *__restrict__ words_out,
+               char *work_base, size_t work_stride, int tables_in_smem, int32_t *__restrict__ words_out,
                int32_t *__restrict__ n_words_out, float *__restrict__ weight_out) {
   __shared__ int s_ntok[2], s_nfront[2], s_log, s_err, s_unres;
   __shared__ unsigned long long s_min;
@@ -141,15 +142,6 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
     w.frontier[i] = reinterpret_cast<int *>(wp); wp += sizeof(int) * max_tok;
   }
   w.inq = reinterpret_cast<int *>(wp); wp += sizeof(int) * H;
-  // two log-likelihood rows (this frame's and the next one's, fetched with cp.async while this
-  // frame is searched) follow the tables in shared memory when they fit
-  float *s_row[2] = {nullptr, nullptr};
-  if (rows_in_smem) {
-    char *rp = tables_in_smem ? wp : s_tab;
-    rp = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(rp) + 15) & ~static_cast<uintptr_t>(15));
-    s_row[0] = reinterpret_cast<float *>(rp);
-    s_row[1] = s_row[0] + ((num_pdfs + 3) & ~3);
-  }
   if (tables_in_smem) wp = gp;  // the global workspace then holds the word records only
   w.log_prev = reinterpret_cast<int *>(wp); wp += sizeof(int) * max_log;
   w.log_ol = reinterpret_cast<int *>(wp);
@@ -166,6 +158,7 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
     }
     __syncthreads();
   }
+  constexpr int kVitGroups = kVitThreads / kVitGroup;
   const int grp = tid / kVitGroup, gl = tid % kVitGroup;
 
   // Epsilon closure of table `c` (ProcessNonemitting, src/decoder.cc:203-237) under `cutoff`, then
@@ -285,20 +278,6 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
     __syncthreads();
     close_and_resolve(0, 1, INFINITY);
 
-    // 16-byte chunks of one row (rows_in_smem requires num_pdfs % 4 == 0: every row is 16-byte aligned)
-    auto fetch_row = [&](int f) {
-      if (f < T) {
-        const float *src = ll0 + static_cast<int64_t>(f) * num_pdfs;
-        float *dst = s_row[f & 1];
-        for (int i = tid * 4; i < num_pdfs; i += kVitThreads * 4)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
-                           static_cast<uint32_t>(__cvta_generic_to_shared(dst + i))),
-                       "l"(src + i)
-                       : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (rows_in_smem) fetch_row(0);
     bool alive = true;
     for (int f = 0; f < T && alive && !s_err; ++f) {
       const int prev = cur;
@@ -306,11 +285,6 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
       const Tab &tp = w.tab[prev], &tc = w.tab[cur];
       const int n_prev = s_ntok[prev];
       const float *ll = ll0 + static_cast<int64_t>(f) * num_pdfs;
-      if (rows_in_smem) {
-        fetch_row(f + 1);  // into the buffer the previous frame is done with (block-wide barriers since)
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        ll = s_row[f & 1];
-      }
       // ---- GetCutoff (src/decoder.cc:141-200) below kBeamSize tokens: best cost + beam
       if (tid == 0) s_min = ~0ull;
       __syncthreads();
@@ -339,7 +313,7 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
             const int il = __ldg(&fst.arc_il[a]);
             if (il == 0) continue;
             const int pdf = __ldg(&tid2pdf[il]);
-            const float ac = -(rows_in_smem ? ll[pdf] : __ldg(&ll[pdf]));
+            const float ac = -__ldg(&ll[pdf]);
             const double total = static_cast<double>(cost) + static_cast<double>(__ldg(&fst.arc_w[a])) +
                                  static_cast<double>(ac);
             m = min(m, ord64(total));
@@ -363,7 +337,7 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
           const int il = __ldg(&fst.arc_il[a]);
           if (il == 0) continue;
           const int pdf = __ldg(&tid2pdf[il]);
-          const float ac = -(rows_in_smem ? ll[pdf] : __ldg(&ll[pdf]));
+          const float ac = -__ldg(&ll[pdf]);
           const double total = static_cast<double>(cost) + static_cast<double>(__ldg(&fst.arc_w[a])) +
                                static_cast<double>(ac);
           if (total > next_cutoff) continue;
@@ -378,7 +352,6 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
       clear_tab(prev);
     }
 
-    if (rows_in_smem) asm volatile("cp.async.wait_group 0;" ::: "memory");
     // ---- BestPath (src/decoder.cc:300-339)
     if (tid == 0) s_min = ~0ull;
     __syncthreads();
@@ -548,12 +521,12 @@ int launch_viterbi(Ctx *c, const pkb_fst *fst, const ViterbiConfig &cfg, const f
     viterbi_init_kernel<<<dim3(4, grid), 256, 0, c->stream>>>(work->as<char>(), stride, 2 * H);
     PKB_CUDA(cudaGetLastError());
   }
-  const size_t row_bytes = 2 * sizeof(float) * static_cast<size_t>((num_pdfs + 3) & ~3) + 16;
-  const bool rows = (num_pdfs % 4) == 0 && (small ? table_bytes : 0) + row_bytes <= 96 * 1024;
-  const size_t dyn_smem = (small ? table_bytes : 0) + (rows ? row_bytes : 0);
-  if (dyn_smem > 48 * 1024)
-    PKB_CUDA(cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(dyn_smem)));
+  // (staging each frame's log-likelihood row in shared memory with cp.async was measured slower,
+  // 44 vs 26 ms for 128 utterances: the larger carve-out takes the L1 space that keeps the FST hot)
+  static const char *env_group = getenv("PKB_VIT_GROUP");  // tuning knob: 8 or 32
+  const size_t dyn_smem = small ? table_bytes : 0;
+  const bool wide = env_group ? atoi(env_group) == 32
+                              : static_cast<double>(fst->num_arcs) >= 12.0 * fst->num_states;
   FstDev fd;
   fd.num_states = fst->num_states;
   fd.start = fst->start;
@@ -566,11 +539,19 @@ int launch_viterbi(Ctx *c, const pkb_fst *fst, const ViterbiConfig &cfg, const f
   fd.arc_ol = fst->d_arc_ol;
   fd.arc_w = fst->d_arc_w;
   LaunchScope scope(c, PKB_KERNEL_MISC);
-  viterbi_kernel<<<grid, kVitThreads, dyn_smem, c->stream>>>(fd, cfg.beam, max_tok, H - 1, cfg.max_log,
-                                                             cfg.max_words, d_loglik, num_pdfs, d_row_off,
-                                                             d_num_frames, n_utts, d_tid2pdf, work->as<char>(),
-                                                             stride, small ? 1 : 0, rows ? 1 : 0, d_words, d_n_words,
-                                                             d_weight);
+#define PKB_VIT_LAUNCH(G)                                                                                  \
+  do {                                                                                                     \
+    if (dyn_smem > 48 * 1024)                                                                              \
+      PKB_CUDA(cudaFuncSetAttribute(viterbi_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                    static_cast<int>(dyn_smem)));                                          \
+    viterbi_kernel<G><<<grid, kVitThreads, dyn_smem, c->stream>>>(                                         \
+        fd, cfg.beam, max_tok, H - 1, cfg.max_log, cfg.max_words, d_loglik, num_pdfs, d_row_off,           \
+        d_num_frames, n_utts, d_tid2pdf, work->as<char>(), stride, small ? 1 : 0, d_words, d_n_words,      \
+        d_weight);                                                                                         \
+  } while (0)
+  if (wide) PKB_VIT_LAUNCH(32);
+  else PKB_VIT_LAUNCH(8);
+#undef PKB_VIT_LAUNCH
   PKB_CUDA(cudaGetLastError());
   return PKB_OK;
 }

@@ -393,6 +393,13 @@ def run_gpu_arm(args, cfg):
 
     # ---- end to end through the host-buffer API: pinned PCM in, log-likelihoods out, per chunk
     e2e = None if args.no_e2e else run_e2e(env, cfg, am, n_utts, batch)
+    if e2e is not None:
+        try:
+            ceil = d2h_ceiling(env)
+            e2e["d2h_ceiling"] = ceil
+            e2e["d2h_frac_of_ceiling"] = e2e["d2h_gbs_per_gpu"] / ceil["per_gpu_gbs"]
+        except Exception as ex:  # torch is plumbing here; the measurement is optional
+            e2e["d2h_ceiling"] = {"unavailable": str(ex)}
     e2e_decode = None
     if cfg["nnet"] and not args.no_e2e:
         e2e_decode = run_e2e_decode(env, cfg, n_utts)
@@ -584,6 +591,31 @@ def run_e2e(env, cfg, am, n_utts, main_batch=None):
             "finite": fin, "timing": "host wall clock over both streams (>= the CUDA-event time of stream 0)",
             "api": "2 x (pkb_batch_set_pcm_i16 + pkb_batch_run + pkb_batch_get_rows), pinned host "
                    "buffers, two contexts alternating so D2H overlaps the next chunk"}
+
+
+def d2h_ceiling(env, gib=1, reps=3):
+    """What this box gives N ranks copying device -> pinned host memory at the same time (plain
+    cudaMemcpyAsync of 1 GiB per rank, no kernels): the ceiling of the e2e leg, whose result bytes
+    cross the same links. Aggregate = bytes of all ranks / max-over-ranks time."""
+    import torch
+    dev = torch.device("cuda", env.local)
+    n = gib << 30
+    src = torch.empty(n, dtype=torch.uint8, device=dev)
+    dst = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    barrier(env.dist, env.local)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    ms = (time.perf_counter() - t0) * 1e3
+    barrier(env.dist, env.local)
+    ms_max, total = reduce_timing(env.dist, env.local, ms, float(n) * reps)
+    del src, dst
+    torch.cuda.empty_cache()
+    return {"aggregate_gbs": total / (ms_max * 1e-3) / 1e9, "per_gpu_gbs": total / env.world / (ms_max * 1e-3) / 1e9,
+            "how": "%d rank(s) x %d x %d GiB cudaMemcpyAsync device -> pinned host at the same time" % (env.world, reps, gib)}
 
 
 def run_e2e_decode(env, cfg, n_utts):

@@ -4,7 +4,10 @@ Emulates `tcgen05.mma kind::f16` (16-bit operands, exact products, FP32 accumula
 float32 matmuls over operands rounded to FP16 / BF16, and compares the resulting scaled
 log-likelihoods (src/am.cc:106-112) with a float64 evaluation of the same net. A policy is a
 per-layer list of (activation planes, weight planes): (1,1) = one MMA per product, (1,2) =
-a_hi*(w_hi+w_lo) and (2,1) = (a_hi+a_lo)*w_hi two MMAs, (2,2) = three MMAs (BF16X3 / FP16X3).
+a_hi*(w_hi+w_lo) and (2,1) = (a_hi+a_lo)*w_hi two MMAs, (2,2) = three MMAs (BF16X3 / FP16X3),
+"c" = that operand's first-order correction through FP8 (E4M3) planes at half the cost (FP16C8).
+This is the experiment behind the choice of PKB_PREC_FP16C8 as the default precision of bench.py
+(DESIGN.md section 1).
 
 Usage: python tools/precision_sim.py [--net 3|4] [--utts N] [--policy NAME ...]
 Test tooling only: it uses the CPU oracle for the front end.

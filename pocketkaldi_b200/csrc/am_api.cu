@@ -590,12 +590,8 @@ int pkb_batch_create(pkb_ctx_t *c, pkb_am_t *am, int n_utts, const int32_t *num_
                                                          am->num_pdfs * sizeof(float)))) != PKB_OK)
         break;
       if (!pad_off.empty() &&
-          cudaMemcpy(ws.pad_off.p, pad_off.data(), pad_off.size() * sizeof(int64_t),
-                     cudaMemcpyHostToDevice) != cudaSuccess) {
-        pkb::set_error("pkb_batch_create: pad_off upload failed");
-        rc = PKB_ERR_CUDA;
+          (rc = pkb::upload(c, ws.pad_off.p, pad_off.data(), pad_off.size() * sizeof(int64_t))) != PKB_OK)
         break;
-      }
       // zero the planes once: rows of empty utterances are never written
       cudaMemsetAsync(ws.feat_hi.p, 0, plane_bytes, c->stream);
       if (am->planes == 2) cudaMemsetAsync(ws.feat_lo.p, 0, plane_bytes, c->stream);
@@ -880,6 +876,9 @@ int pkb_batch_decode(pkb_batch_t *b, const pkb_fst_t *fst, float beam, int max_t
   PKB_REQUIRE(fst->c == b->c, "pkb_batch_decode: the FST belongs to another context");
   PKB_REQUIRE(!b->compact, "pkb_batch_decode: reads the FP32 log-likelihoods (switch the compact output off)");
   PKB_REQUIRE(!b->am->tid2pdf.empty(), "pkb_batch_decode: the model has no tid2pdf map");
+  PKB_REQUIRE(fst->max_ilabel < static_cast<int>(b->am->tid2pdf.size()),
+              "pkb_batch_decode: the graph uses input label %d but the model's tid2pdf map has %zu entries",
+              fst->max_ilabel, b->am->tid2pdf.size());
   PKB_REQUIRE(max_words > 0 && words_out && n_words_out && weight_out, "pkb_batch_decode: bad output arguments");
   Ctx *c = b->c;
   PKB_CUDA(cudaSetDevice(c->device));

@@ -105,6 +105,12 @@ struct Ctx {
   std::vector<cudaEvent_t> free_events;
 };
 
+// Host -> device upload ordered on the context stream and complete on return. Plain cudaMemcpy
+// from pageable memory may return before the DMA has landed, and the context stream is
+// non-blocking (no implicit ordering against the legacy stream), so a kernel queued right after it
+// could read stale bytes.
+int upload(Ctx *c, void *dst, const void *src, size_t bytes);
+
 // Reports (and clears) an error word left by a kernel; call after a stream synchronisation.
 int check_device_error(Ctx *c, const char *who);
 

@@ -1,6 +1,7 @@
 // Context, error plumbing, batch metadata, timers and launch accounting of libpkb200.
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -36,6 +37,9 @@ int DevBuf::ensure(size_t bytes) {
     return PKB_ERR_CUDA;
   }
   cap = want;
+  // PKB_ALLOC_FILL=<byte>: debugging aid that makes reads of never-written device memory deterministic
+  static const char *fill = getenv("PKB_ALLOC_FILL");
+  if (fill != nullptr) cudaMemset(p, atoi(fill), want);
   return PKB_OK;
 }
 
@@ -43,6 +47,13 @@ void DevBuf::release() {
   if (p) cudaFree(p);
   p = nullptr;
   cap = 0;
+}
+
+int upload(Ctx *c, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return PKB_OK;
+  PKB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  PKB_CUDA(cudaStreamSynchronize(c->stream));
+  return PKB_OK;
 }
 
 int check_device_error(Ctx *c, const char *who) {

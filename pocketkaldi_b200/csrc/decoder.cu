@@ -435,6 +435,7 @@ int fst_build(Ctx *c, int num_states, int start, const float *final_w, const int
     }
   }
   bool has_eps = false;
+  int max_il = 0;
   std::vector<int32_t> dst(num_arcs), il(num_arcs), ol(num_arcs);
   std::vector<float> wt(num_arcs);
   for (int s = 0; s < num_states; ++s)
@@ -447,6 +448,7 @@ int fst_build(Ctx *c, int num_states, int start, const float *final_w, const int
     PKB_REQUIRE(dst[a] >= 0 && dst[a] < num_states, "pkb_fst: arc %d leads to state %d", a, dst[a]);
     PKB_REQUIRE(il[a] >= 0, "pkb_fst: arc %d has a negative input label", a);
     has_eps = has_eps || il[a] == 0;
+    max_il = std::max(max_il, il[a]);
   }
   pkb_fst *f = new pkb_fst();
   f->c = c;
@@ -454,6 +456,7 @@ int fst_build(Ctx *c, int num_states, int start, const float *final_w, const int
   f->num_arcs = num_arcs;
   f->start = start;
   f->has_eps = has_eps;
+  f->max_ilabel = max_il;
   const size_t n1 = static_cast<size_t>(num_states) + 1, na = std::max(num_arcs, 1);
   const size_t bytes = 4 * (static_cast<size_t>(num_states) + n1 + 5 * na);
   std::vector<char> host(bytes, 0);
@@ -470,10 +473,7 @@ int fst_build(Ctx *c, int num_states, int start, const float *final_w, const int
     memcpy(h + o_w, wt.data(), 4 * static_cast<size_t>(num_arcs));
   }
   int rc = f->buf.ensure(bytes);
-  if (rc == PKB_OK && cudaMemcpy(f->buf.p, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
-    set_error("pkb_fst: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    rc = PKB_ERR_CUDA;
-  }
+  if (rc == PKB_OK) rc = upload(c, f->buf.p, h, bytes);
   if (rc != PKB_OK) {
     f->buf.release();
     delete f;

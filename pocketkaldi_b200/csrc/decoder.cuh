@@ -14,6 +14,7 @@ struct pkb_fst {
   pkb::Ctx *c = nullptr;
   int num_states = 0, num_arcs = 0, start = 0;
   bool has_eps = false;  // some arc has input label 0
+  int max_ilabel = 0;    // largest input label (must index the model's tid2pdf map)
   pkb::DevBuf buf;       // one allocation, pointers below
   const float *d_final = nullptr;      // [num_states]
   const int32_t *d_arc_begin = nullptr;  // [num_states + 1]: arcs of state s are [begin[s], begin[s + 1])

@@ -455,7 +455,7 @@ int build_fbank_tables(Ctx *c) {
   memcpy(&host[off_melc], melc.data(), sizeof(uint32_t) * 32);
   memcpy(&host[off_mels], mels.data(), sizeof(uint32_t) * kMel);
   PKB_TRY(c->tables.ensure(total));
-  PKB_CUDA(cudaMemcpy(c->tables.p, host.data(), total, cudaMemcpyHostToDevice));
+  PKB_TRY(upload(c, c->tables.p, host.data(), total));
   char *base = c->tables.as<char>();
   c->fb.hamming = reinterpret_cast<const float *>(base + off_ham);
   c->fb.tw_pass = reinterpret_cast<const float2 *>(base + off_twp);

@@ -140,13 +140,13 @@ int pack_stage(Ctx *c, Stage *st, const float *W, const float *b, int out_dim, i
   std::vector<float> bias(st->n_pad, 0.0f);
   memcpy(bias.data(), b, sizeof(float) * out_dim);
   PKB_TRY(st->w_hi.ensure(elems * 2));
-  PKB_CUDA(cudaMemcpy(st->w_hi.p, hi.data(), elems * 2, cudaMemcpyHostToDevice));
+  PKB_TRY(upload(c, st->w_hi.p, hi.data(), elems * 2));
   if (planes == 2) {
     PKB_TRY(st->w_lo.ensure(elems * 2));
-    PKB_CUDA(cudaMemcpy(st->w_lo.p, lo.data(), elems * 2, cudaMemcpyHostToDevice));
+    PKB_TRY(upload(c, st->w_lo.p, lo.data(), elems * 2));
   }
   PKB_TRY(st->bias.ensure(sizeof(float) * st->n_pad));
-  PKB_CUDA(cudaMemcpy(st->bias.p, bias.data(), sizeof(float) * st->n_pad, cudaMemcpyHostToDevice));
+  PKB_TRY(upload(c, st->bias.p, bias.data(), sizeof(float) * st->n_pad));
   PKB_TRY(make_tensor_map(&st->tm_w_hi, st->w_hi.p, st->k_pad, st->n_pad,
                           static_cast<uint64_t>(st->k_pad) * 2, st->block_n));
   if (planes == 2)
@@ -161,7 +161,6 @@ int pack_stage(Ctx *c, Stage *st, const float *W, const float *b, int out_dim, i
                             static_cast<uint64_t>(st->k_pad) * 2, st->block_n / 2));
   else
     st->tm_w_lo_half = st->tm_w_hi_half;
-  (void)c;
   return PKB_OK;
 }
 
@@ -190,14 +189,14 @@ int pack_stage_c8(Ctx *c, Stage *st, const float *W, const float *b, int out_dim
   PKB_TRY(st->w8_hi.ensure(e8));
   PKB_TRY(st->w8_lo.ensure(e8));
   PKB_TRY(st->bias.ensure(sizeof(float) * st->n_pad));
-  PKB_CUDA(cudaMemcpy(st->bias.p, bias.data(), sizeof(float) * st->n_pad, cudaMemcpyHostToDevice));
+  PKB_TRY(upload(c, st->bias.p, bias.data(), sizeof(float) * st->n_pad));
   {
     // the planes are rounded on the device: 2 x 8.8 M scalar FP8 conversions on the host would
     // dominate the model load of the config-3 net
     DevBuf tmp;
     const size_t wbytes = static_cast<size_t>(out_dim) * in_dim * sizeof(float);
     PKB_TRY(tmp.ensure(wbytes));
-    PKB_CUDA(cudaMemcpy(tmp.p, W, wbytes, cudaMemcpyHostToDevice));
+    PKB_TRY(upload(c, tmp.p, W, wbytes));
     const int64_t threads = static_cast<int64_t>(e8);
     pack_c8_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(
         tmp.as<float>(), out_dim, in_dim, st->n_pad, st->k_pad, st->k_pad8, sg, st->w_hi.as<__nv_bfloat16>(),
@@ -334,12 +333,7 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
     if (prior)
       for (int j = 0; j < am->num_pdfs; ++j) lp[j] = static_cast<float>(log(static_cast<double>(prior[j])));
     rc = am->log_prior.ensure(sizeof(float) * lp_len);
-    if (rc == PKB_OK &&
-        cudaMemcpy(am->log_prior.p, lp.data(), sizeof(float) * lp_len,
-                   cudaMemcpyHostToDevice) != cudaSuccess) {
-      set_error("log prior upload failed");
-      rc = PKB_ERR_CUDA;
-    }
+    if (rc == PKB_OK) rc = upload(c, am->log_prior.p, lp.data(), sizeof(float) * lp_len);
   }
   if (rc == PKB_OK) {
     const int w = left + right + 1;

@@ -53,3 +53,23 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "libpkoracle" not in src and "libpkref" not in src, f
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_loglik16_expand_is_host_only_and_exact():
+    # pkb_loglik16_expand finishes the compact rows on the host (no GPU involved):
+    # out = prob_scale * (half(h) + off[frame])
+    import ctypes as C
+    import numpy as np
+    from pocketkaldi_b200 import binding
+    lib = binding.load_library()
+    rng = np.random.default_rng(0)
+    h = rng.uniform(-40, 0, (37, 129)).astype(np.float16)
+    h[0, :4] = [0.0, -0.0, -6.1e-5, -65504.0]          # zero, signed zero, subnormal, largest half
+    off = rng.uniform(-9, -7, 37).astype(np.float32)
+    out = np.empty(h.shape, np.float32)
+    rc = lib.pkb_loglik16_expand(h.view(np.uint16).ctypes.data, off.ctypes.data, 37, 129, C.c_float(0.1),
+                                 out.ctypes.data)
+    assert rc == 0
+    want = (h.astype(np.float32) + off[:, None]) * np.float32(0.1)
+    assert np.array_equal(out, want)
+    assert lib.pkb_loglik16_expand(None, None, 0, 129, C.c_float(1.0), None) == 0   # empty block

@@ -175,6 +175,27 @@ def test_fp16c8_linear_layers_alone(ctx):
         assert e8 < 1.5e-4 and e8 < e1 / 4
 
 
+def test_model_creation_is_reproducible(ctx):
+    # regression: the FP16C8 weight planes of small layers were once packed from a staging buffer
+    # whose upload had not landed yet (pageable cudaMemcpy + a non-blocking stream); every instance
+    # of the same model must give bit-identical results
+    rng = np.random.default_rng(23)
+    layers = formats.make_dnn(rng, 440, 320, 1, 1000)
+    prior = np.full(1000, 1e-3, np.float32)
+    feats = [(rng.standard_normal((n, 40)) * 2.5).astype(np.float32) for n in (300, 1, 420)]
+    first = None
+    for prec in (pk.PREC_FP16C8, pk.PREC_BF16X3):
+        first = None
+        for _ in range(6):
+            am = pk.AcousticModel(ctx, prec).from_layers(layers, prior, 5, 5)
+            outs = am.compute_batch(feats)
+            am.close()
+            if first is None:
+                first = outs
+            else:
+                assert all(np.array_equal(a, b) for a, b in zip(first, outs))
+
+
 def test_fused_pcm_to_loglik(ctx, golden, toy_conf):
     am = pk.AcousticModel(ctx, pk.PREC_BF16X3).Read(toy_conf)
     pcms = [golden["hello_pcm"], golden["cat_pcm"], synth_pcm(1234, [0], 160000)[0],

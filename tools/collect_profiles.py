@@ -1,0 +1,100 @@
+"""Turns the scratch output of tools/gpu_final.sh (gpurun_out/) into the tracked round-2 evidence under
+profiles/: bench JSONs, the ncu launch list with per-kernel shares, front-end ncu details."""
+import csv
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+
+def load(path):
+    for line in open(path):
+        if line.startswith("{"):
+            return json.loads(line)
+
+
+def main():
+    for src, dst in (("bench_default.json", "r2_bench_default.json"), ("bench_reference.json", "r2_bench_reference_arm.json"),
+                     ("bench_config2.json", "r2_bench_config2.json"), ("bench_config4.json", "r2_bench_config4.json"),
+                     ("bench_config5.json", "r2_bench_config5.json")):
+        if os.path.exists(os.path.join(G, src)):
+            json.dump(load(os.path.join(G, src)), open(os.path.join(P, dst), "w"))
+    if os.path.exists(os.path.join(G, "decode_demo.txt")):
+        head = ("python tools/decode_demo.py --utts 128 --ref --precision fp16c8   (B200 box, 16 host cores; wall clock of the\n"
+                "whole process: CUDA init, model load of the 85 MB config-3 net, list ingestion, acoustic scores, Viterbi, printing)\n"
+                "model: splice +-5 -> 6x1024 ReLU -> 3000 pdfs (random init), 40-word loop graph; 128 synthetic 10 s utterances\n\n")
+        open(os.path.join(P, "r2_decode_demo.txt"), "w").write(head + open(os.path.join(G, "decode_demo.txt")).read())
+    if os.path.exists(os.path.join(G, "smoke_launches.csv")):
+        shutil.copy(os.path.join(G, "smoke_launches.csv"), os.path.join(P, "r2_smoke_ncu_launches.csv"))
+    # ---- launch list of the default bench (2 steps + 1 warm-up, cold-cache serialised kernels)
+    lp = os.path.join(G, "launches.csv")
+    if os.path.exists(lp):
+        rows = [r for r in csv.reader(open(lp)) if len(r) > 10]
+        h = rows[0]
+        ik, iv = h.index("Kernel Name"), h.index("Metric Value")
+        with open(os.path.join(P, "r2_launches.csv"), "w") as fd:
+            w = csv.writer(fd)
+            w.writerow(["ID", "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum [ns]"])
+            for r in rows[1:]:
+                w.writerow([r[h.index("ID")], r[ik], r[h.index("Grid Size")], r[h.index("Block Size")], r[iv]])
+        cls = {"fbank": 0.0, "cmvn": 0.0, "gemm hidden": 0.0, "gemm output": 0.0, "other": 0.0}
+        n = dict.fromkeys(cls, 0)
+        for r in rows[1:]:
+            k, t = r[ik], float(r[iv].replace(",", ""))
+            if "fbank_kernel" in k:
+                c = "fbank"
+            elif "cmvn_kernel" in k:
+                c = "cmvn"
+            elif "gemm_kernel" in k:
+                c = "gemm output" if ", 1, " in k.split("gemm_kernel<")[1].split(">")[0] and k.split("gemm_kernel<")[1].split(",")[2].strip() == "1" else "gemm hidden"
+            else:
+                c = "other"
+            cls[c] += t
+            n[c] += 1
+        tot = sum(v for k, v in cls.items() if k != "other")
+        b = load(os.path.join(G, "bench_default.json"))
+        km = b["kernel_ms_per_step"]
+        ev = {"fbank": km["fbank"], "cmvn": km["cmvn"], "gemm hidden": km["gemm"], "gemm output": km["gemm_final"], "other": km["misc"]}
+        evt = sum(ev.values())
+        with open(os.path.join(P, "r2_launch_shares.txt"), "w") as fd:
+            fd.write("Share of the step per kernel class: ncu launch list (profiles/r2_launches.csv: cold cache, serialised,\n"
+                     "unthrottled clocks, 3 passes of the hot path) against the CUDA-event times of the timed region of\n"
+                     "profiles/r2_bench_default.json (power-capped step). Rule 4: the shares must agree, not the absolutes.\n\n")
+            fd.write("%-14s %10s %10s %12s %12s\n" % ("class", "launches", "ncu ms", "ncu share", "event share"))
+            for c in cls:
+                if c == "other":
+                    fd.write("%-14s %10d %10.3f   (set-up kernels outside the timed region: weight packing, row map,\n"
+                             "%s synthetic PCM, checksum)\n" % ("set-up", n[c], cls[c] / 1e6, " " * 37))
+                else:
+                    fd.write("%-14s %10d %10.3f %11.1f%% %11.1f%%\n" % (c, n[c], cls[c] / 1e6, 100 * cls[c] / tot, 100 * ev[c] / evt))
+        print(open(os.path.join(P, "r2_launch_shares.txt")).read())
+    # ---- front-end ncu details (final kernels)
+    rep = os.path.join(G, "r2_front.ncu-rep")
+    if os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE).stdout.decode()
+        rows = list(csv.reader(raw.splitlines()))
+        h, u = rows[0], rows[1]
+        keep = [k for k in h if k in (
+            "Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+            "gpu__time_duration.sum", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "l1tex__throughput.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed_pipe_fp64.sum",
+            "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct") or ("issue_stalled" in k and "per_issue_active" in k)]
+        with open(os.path.join(P, "r2_ncu_front.csv"), "w") as fd:
+            w = csv.writer(fd)
+            w.writerow(keep)
+            w.writerow([u[h.index(k)] for k in keep])
+            for r in rows[2:]:
+                w.writerow([r[h.index(k)] for k in keep])
+        print("front-end details:", len(rows) - 2, "kernels")
+
+
+if __name__ == "__main__":
+    main()

@@ -244,7 +244,9 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
         tc.bp[slot] = pb;
       }
       __syncthreads();
-      if (s_unres == 0) break;
+      const int unres = s_unres;  // read by everyone before thread 0 may reset it in the next pass
+      __syncthreads();
+      if (unres == 0) break;
       if (pass == 255 && tid == 0) s_err = 3;
     }
     __syncthreads();
@@ -406,6 +408,251 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small graphs (pocketkaldi's own territory: command / small-vocabulary grammars): every state has a
+// slot, so the token table is three dense shared-memory arrays per frame and the search runs
+// arc-parallel over the whole FST -- all lanes busy, 32-bit native shared-memory atomics, each
+// thread keeps the totals of its arcs in registers across the passes of a frame.
+//   cost[s]  ord32(token cost), kInactive when the state holds no token
+//   warc[s]  winning arc; epsilon arcs carry bit 31 so that an emitting arc of equal cost wins, as
+//            it does in the reference where emitting arcs are inserted first (src/decoder.cc:127-134)
+//   bp[s]    newest word record of the token
+constexpr uint32_t kInactive = 0xffffffffu;
+
+template <int kArcsPerThread>
+__global__ void __launch_bounds__(kVitThreads)
+viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_words,
+                     const float *__restrict__ loglik, int num_pdfs, const int64_t *__restrict__ row_off,
+                     const int32_t *__restrict__ num_frames, int n_utts, const int32_t *__restrict__ tid2pdf,
+                     char *work_base, size_t work_stride, int32_t *__restrict__ words_out,
+                     int32_t *__restrict__ n_words_out, float *__restrict__ weight_out) {
+  extern __shared__ __align__(16) char s_dense[];
+  __shared__ int s_log, s_err, s_unres, s_changed;
+  __shared__ unsigned long long s_min;
+  const int S = fst.num_states;
+  uint32_t *cost[2], *warc[2];
+  int *bp[2];
+  {
+    uint32_t *p = reinterpret_cast<uint32_t *>(s_dense);
+    cost[0] = p; cost[1] = p + S; warc[0] = p + 2 * S; warc[1] = p + 3 * S;
+    bp[0] = reinterpret_cast<int *>(p + 4 * S); bp[1] = reinterpret_cast<int *>(p + 5 * S);
+  }
+  int *log_prev = reinterpret_cast<int *>(work_base + static_cast<size_t>(blockIdx.x) * work_stride);
+  int *log_ol = log_prev + max_log;
+  const int tid = threadIdx.x;
+
+  // this thread's arcs (the same in every pass of every frame)
+  int a_src[kArcsPerThread], a_dst[kArcsPerThread], a_il[kArcsPerThread];
+  float a_w[kArcsPerThread];
+#pragma unroll
+  for (int k = 0; k < kArcsPerThread; ++k) {
+    const int a = tid + k * kVitThreads;
+    const bool ok = a < num_arcs;
+    a_src[k] = ok ? __ldg(&fst.arc_src[a]) : -1;
+    a_dst[k] = ok ? __ldg(&fst.arc_dst[a]) : 0;
+    a_il[k] = ok ? __ldg(&fst.arc_il[a]) : 0;
+    a_w[k] = ok ? __ldg(&fst.arc_w[a]) : 0.0f;
+  }
+
+  // epsilon closure of frame table c under `cutoff`, winners, word back-pointers
+  auto finish_frame = [&](int c, int p, double cutoff, const double (&td)[kArcsPerThread], const bool (&live)[kArcsPerThread]) {
+    if (fst.has_eps) {
+      for (int round = 0; round < 4096; ++round) {
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kArcsPerThread; ++k) {
+          if (a_src[k] < 0 || a_il[k] != 0) continue;
+          const uint32_t cs = *reinterpret_cast<volatile uint32_t *>(&cost[c][a_src[k]]);
+          if (cs == kInactive) continue;
+          const double total = static_cast<double>(unord32(cs)) + static_cast<double>(a_w[k]);
+          if (total > cutoff) continue;
+          const uint32_t o = ord32(static_cast<float>(total));
+          if (atomicMin(&cost[c][a_dst[k]], o) > o) s_changed = 1;
+        }
+        __syncthreads();
+        const int changed = s_changed;  // read by everyone before thread 0 resets it
+        __syncthreads();
+        if (!changed) break;
+      }
+    }
+    // winners against the final costs: emitting arcs from the totals kept in registers, epsilon
+    // arcs from their source's final cost
+#pragma unroll
+    for (int k = 0; k < kArcsPerThread; ++k) {
+      if (a_src[k] < 0) continue;
+      const uint32_t a = static_cast<uint32_t>(tid + k * kVitThreads);
+      if (a_il[k] != 0) {
+        if (live[k] && ord32(static_cast<float>(td[k])) == cost[c][a_dst[k]]) atomicMin(&warc[c][a_dst[k]], a);
+      } else if (fst.has_eps) {
+        const uint32_t cs = cost[c][a_src[k]];
+        if (cs == kInactive) continue;
+        const double total = static_cast<double>(unord32(cs)) + static_cast<double>(a_w[k]);
+        if (total <= cutoff && ord32(static_cast<float>(total)) == cost[c][a_dst[k]])
+          atomicMin(&warc[c][a_dst[k]], a | 0x80000000u);
+      }
+    }
+    __syncthreads();
+    // word back-pointers (Decoder::InsertTok, src/decoder.cc:107-117)
+    for (int s = tid; s < S; s += kVitThreads) bp[c][s] = cost[c][s] != kInactive ? -2 : -1;
+    for (int pass = 0; pass < 256; ++pass) {
+      if (tid == 0) s_unres = 0;
+      __syncthreads();
+      for (int s = tid; s < S; s += kVitThreads) {
+        if (bp[c][s] != -2) continue;
+        const uint32_t wa = warc[c][s];
+        int pb;
+        if (wa == kInactive) {
+          pb = -1;  // the start token
+        } else {
+          const int a = static_cast<int>(wa & 0x7fffffffu);
+          const int src = __ldg(&fst.arc_src[a]);
+          if (wa >> 31) {
+            pb = *reinterpret_cast<volatile int *>(&bp[c][src]);
+            if (pb == -2) { atomicAdd(&s_unres, 1); continue; }
+          } else {
+            pb = bp[p][src];
+          }
+          const int ol = __ldg(&fst.arc_ol[a]);
+          if (ol != 0) {
+            const int r = atomicAdd(&s_log, 1);
+            if (r >= max_log) { s_err = 2; pb = -1; }
+            else { log_prev[r] = pb; log_ol[r] = ol; pb = r; }
+          }
+        }
+        bp[c][s] = pb;
+      }
+      __syncthreads();
+      const int unres = s_unres;
+      __syncthreads();
+      if (unres == 0) break;
+      if (pass == 255 && tid == 0) s_err = 3;
+    }
+    __syncthreads();
+  };
+
+  for (int u = blockIdx.x; u < n_utts; u += gridDim.x) {
+    const int T = num_frames[u];
+    const float *ll0 = loglik + row_off[u] * num_pdfs;
+    for (int s = tid; s < S; s += kVitThreads) {
+      cost[0][s] = cost[1][s] = kInactive;
+      warc[0][s] = warc[1][s] = kInactive;
+      bp[0][s] = bp[1][s] = -1;
+    }
+    if (tid == 0) { s_log = 0; s_err = 0; }
+    __syncthreads();
+    // ---- InitDecoding (src/decoder.cc:82-101)
+    int cur = 0;
+    if (tid == 0) cost[0][fst.start] = ord32(0.0f);
+    __syncthreads();
+    {
+      double td[kArcsPerThread];
+      bool live[kArcsPerThread];
+#pragma unroll
+      for (int k = 0; k < kArcsPerThread; ++k) { td[k] = 0.0; live[k] = false; }
+      finish_frame(0, 1, INFINITY, td, live);
+    }
+    bool alive = true;
+    for (int f = 0; f < T && alive && !s_err; ++f) {
+      const int prev = cur;
+      cur ^= 1;
+      const float *ll = ll0 + static_cast<int64_t>(f) * num_pdfs;
+      // ---- GetCutoff below kBeamSize tokens
+      if (tid == 0) s_min = ~0ull;
+      __syncthreads();
+      {
+        uint32_t m = kInactive;
+        for (int s = tid; s < S; s += kVitThreads) m = min(m, cost[prev][s]);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((tid & 31) == 0) atomicMin(&s_min, static_cast<unsigned long long>(m));
+      }
+      __syncthreads();
+      if (static_cast<uint32_t>(s_min) == kInactive) { alive = false; break; }
+      const float weight_cutoff =
+          static_cast<float>(static_cast<double>(unord32(static_cast<uint32_t>(s_min))) + static_cast<double>(beam));
+      __syncthreads();
+      if (tid == 0) s_min = ~0ull;
+      __syncthreads();
+      // ---- ProcessEmitting, pass 1: totals of this thread's arcs, bound on the next frame
+      double td[kArcsPerThread];
+      bool live[kArcsPerThread];
+      {
+        unsigned long long m = ~0ull;
+#pragma unroll
+        for (int k = 0; k < kArcsPerThread; ++k) {
+          live[k] = false;
+          td[k] = 0.0;
+          if (a_src[k] < 0 || a_il[k] == 0) continue;
+          const uint32_t cs = cost[prev][a_src[k]];
+          if (cs == kInactive) continue;
+          const float c = unord32(cs);
+          if (c > weight_cutoff) continue;
+          const float ac = -__ldg(&ll[__ldg(&tid2pdf[a_il[k]])]);
+          td[k] = static_cast<double>(c) + static_cast<double>(a_w[k]) + static_cast<double>(ac);
+          live[k] = true;
+          m = min(m, ord64(td[k]));
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((tid & 31) == 0) atomicMin(&s_min, m);
+      }
+      __syncthreads();
+      if (s_min == ~0ull) { alive = false; break; }
+      const double next_cutoff = unord64(s_min) + static_cast<double>(beam);
+      // ---- pass 2: token costs of this frame
+#pragma unroll
+      for (int k = 0; k < kArcsPerThread; ++k) {
+        live[k] = live[k] && td[k] <= next_cutoff;
+        if (live[k]) atomicMin(&cost[cur][a_dst[k]], ord32(static_cast<float>(td[k])));
+      }
+      __syncthreads();
+      finish_frame(cur, prev, static_cast<double>(static_cast<float>(next_cutoff)), td, live);
+      for (int s = tid; s < S; s += kVitThreads) {
+        cost[prev][s] = kInactive;
+        warc[prev][s] = kInactive;
+      }
+      __syncthreads();
+    }
+
+    // ---- BestPath (src/decoder.cc:300-339)
+    if (tid == 0) s_min = ~0ull;
+    __syncthreads();
+    if (alive && !s_err) {
+      for (int s = tid; s < S; s += kVitThreads) {
+        if (cost[cur][s] == kInactive) continue;
+        const float c = unord32(cost[cur][s]) + fst.final_w[s];
+        if (c != INFINITY) atomicMin(&s_min, pack(c, static_cast<uint32_t>(s)));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int32_t *wo = words_out + static_cast<size_t>(u) * max_words;
+      if (s_err) {
+        n_words_out[u] = -s_err;
+        weight_out[u] = 0.0f;
+      } else if (s_min == ~0ull) {
+        n_words_out[u] = 0;
+        weight_out[u] = 0.0f;
+      } else {
+        const int s = static_cast<int>(static_cast<uint32_t>(s_min));
+        float weight = cost_of(s_min);
+        weight += fst.final_w[s];
+        weight_out[u] = weight;
+        int nw = 0;
+        for (int r = bp[cur][s]; r >= 0; r = log_prev[r]) ++nw;
+        n_words_out[u] = nw;
+        int k = nw;
+        for (int r = bp[cur][s]; r >= 0; r = log_prev[r]) {
+          --k;
+          if (k < max_words) wo[k] = log_ol[r];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // the two value arrays lead every block's workspace
 __global__ void viterbi_init_kernel(char *work_base, size_t work_stride, uint32_t n) {
   unsigned long long *vals = reinterpret_cast<unsigned long long *>(work_base + work_stride * blockIdx.y);
@@ -499,6 +746,41 @@ int launch_viterbi(Ctx *c, const pkb_fst *fst, const ViterbiConfig &cfg, const f
   if (n_utts == 0) return PKB_OK;
   PKB_REQUIRE(cfg.max_tokens >= 16 && cfg.max_log >= 16 && cfg.max_words >= 1 && cfg.beam > 0.0f,
               "pkb_batch_decode: bad configuration");
+  FstDev fd;
+  fd.num_states = fst->num_states;
+  fd.start = fst->start;
+  fd.has_eps = fst->has_eps ? 1 : 0;
+  fd.final_w = fst->d_final;
+  fd.arc_begin = fst->d_arc_begin;
+  fd.arc_src = fst->d_arc_src;
+  fd.arc_dst = fst->d_arc_dst;
+  fd.arc_il = fst->d_arc_il;
+  fd.arc_ol = fst->d_arc_ol;
+  fd.arc_w = fst->d_arc_w;
+  static const char *env_dense = getenv("PKB_VIT_DENSE");  // tuning knob: 0 forces the table kernel
+  if (fst->num_states <= 2048 && fst->num_arcs <= 16 * kVitThreads && !(env_dense && atoi(env_dense) == 0)) {
+    // dense kernel: no token capacity to run out of; the global workspace holds the word records only
+    const size_t stride = (2 * sizeof(int) * static_cast<size_t>(cfg.max_log) + 255) & ~static_cast<size_t>(255);
+    const int grid = std::min(n_utts, c->sm_count * 4);
+    PKB_TRY(work->ensure(stride * grid));
+    const size_t smem = 6 * sizeof(uint32_t) * static_cast<size_t>(fst->num_states);
+    LaunchScope scope(c, PKB_KERNEL_MISC);
+#define PKB_VIT_DENSE(APT)                                                                               \
+  do {                                                                                                   \
+    if (smem > 48 * 1024)                                                                                \
+      PKB_CUDA(cudaFuncSetAttribute(viterbi_dense_kernel<APT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    static_cast<int>(smem)));                                            \
+    viterbi_dense_kernel<APT><<<grid, kVitThreads, smem, c->stream>>>(                                   \
+        fd, fst->num_arcs, cfg.beam, cfg.max_log, cfg.max_words, d_loglik, num_pdfs, d_row_off,          \
+        d_num_frames, n_utts, d_tid2pdf, work->as<char>(), stride, d_words, d_n_words, d_weight);        \
+  } while (0)
+    if (fst->num_arcs <= 4 * kVitThreads) PKB_VIT_DENSE(4);
+    else if (fst->num_arcs <= 8 * kVitThreads) PKB_VIT_DENSE(8);
+    else PKB_VIT_DENSE(16);
+#undef PKB_VIT_DENSE
+    PKB_CUDA(cudaGetLastError());
+    return PKB_OK;
+  }
   // a graph with at most 512 states can never hold more tokens than states: its tables go to
   // shared memory (capacity = the state count), whatever max_tokens says
   const bool small = fst->num_states <= 512;
@@ -527,17 +809,6 @@ int launch_viterbi(Ctx *c, const pkb_fst *fst, const ViterbiConfig &cfg, const f
   const size_t dyn_smem = small ? table_bytes : 0;
   const bool wide = env_group ? atoi(env_group) == 32
                               : static_cast<double>(fst->num_arcs) >= 12.0 * fst->num_states;
-  FstDev fd;
-  fd.num_states = fst->num_states;
-  fd.start = fst->start;
-  fd.has_eps = fst->has_eps ? 1 : 0;
-  fd.final_w = fst->d_final;
-  fd.arc_begin = fst->d_arc_begin;
-  fd.arc_src = fst->d_arc_src;
-  fd.arc_dst = fst->d_arc_dst;
-  fd.arc_il = fst->d_arc_il;
-  fd.arc_ol = fst->d_arc_ol;
-  fd.arc_w = fst->d_arc_w;
   LaunchScope scope(c, PKB_KERNEL_MISC);
 #define PKB_VIT_LAUNCH(G)                                                                                  \
   do {                                                                                                     \

@@ -37,7 +37,8 @@ sys.path.insert(0, ROOT)
 METRIC = "acoustic frames/s (fbank+CMVN+nnet loglik)"
 # The precision the headline is quoted in. tests/test_gpu_baseline_nets.py asserts the
 # north_star parity bar for this mode on the config-3 and config-4 nets.
-DEFAULT_PRECISION = "fp16c8"
+DEFAULT_PRECISION = "fp16r"
+REFINE_MARGIN = float(os.environ.get("PKB_BENCH_REFINE_MARGIN", "0.04"))  # log-likelihood units; pkb_am_set_refine_margin
 LL_TOL, ARGMAX_MIN, FEAT_TOL = 2e-2, 0.999, 1e-4
 SAMPLES_10S = 160000
 FRAMES_10S = 998
@@ -246,7 +247,7 @@ def run_reference_arm(args, cfg):
 def precision_id(name):
     import pocketkaldi_b200 as pk
     table = {"bf16": pk.PREC_BF16, "bf16x3": pk.PREC_BF16X3, "fp16": pk.PREC_FP16}
-    for k, attr in (("fp16x3", "PREC_FP16X3"), ("fp16c8", "PREC_FP16C8")):
+    for k, attr in (("fp16x3", "PREC_FP16X3"), ("fp16c8", "PREC_FP16C8"), ("fp16r", "PREC_FP16R")):
         if hasattr(pk, attr):
             table[k] = getattr(pk, attr)
     return table[name]
@@ -284,6 +285,8 @@ def measure_batch(env, cfg, precision, n_utts, steps, warmup, sample_clocks):
     am = None
     if cfg["nnet"]:
         am = pk.AcousticModel(ctx, precision_id(precision)).from_layers(make_layers(cfg), uniform_prior(cfg), 5, 5)
+        if precision == "fp16r":
+            am.set_refine_margin(REFINE_MARGIN)
     # the nnet reads the 16-bit operand planes the CMVN kernel writes; the FP32 copy of the
     # features is not part of the path to the log-likelihoods (PKB_STAGE_NO_FEATS)
     stages = (pk.STAGE_ALL | pk.STAGE_NO_FEATS) if cfg["nnet"] else (pk.STAGE_FBANK | pk.STAGE_CMVN)
@@ -312,6 +315,16 @@ def measure_batch(env, cfg, precision, n_utts, steps, warmup, sample_clocks):
 
     gemm_launches = prof["gemm"][0] + prof["gemm_final"][0]
     gemm_ms = prof["gemm"][1] + prof["gemm_final"][1]
+    refine = None
+    if cfg["nnet"] and precision == "fp16r":
+        # the selection, gather and scatter kernels of the second pass belong to the nnet's time
+        gemm_ms += prof["misc"][1]
+        rows, refined = batch.refine_stats()
+        refine = {"margin": REFINE_MARGIN, "gemm_rows": rows, "frames_recomputed": refined,
+                  "fraction_of_frames": refined / max(frames, 1),
+                  "select_gather_scatter_ms_per_step": prof["misc"][1] / steps,
+                  "how": "pass 1: one FP16 MMA per product for every frame; pass 2: FP16C8 operands for the "
+                         "frames whose two best pdfs are closer than the margin (include/pkb200.h)"}
     fb_ms = prof["fbank"][1] + prof["cmvn"][1]
     front_gbs = 480.0 * frames * steps / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else None
     cmvn_gbs = 320.0 * frames * steps / (prof["cmvn"][1] * 1e-3) / 1e9 if prof["cmvn"][1] > 0 else None
@@ -337,7 +350,8 @@ def measure_batch(env, cfg, precision, n_utts, steps, warmup, sample_clocks):
                                             * steps / (prof["gemm"][1] * 1e-3) / 1e12,
                     "output_layer_tflops": 2 * cfg["width"] * cfg["pdfs"] * frames * steps
                                            / (prof["gemm_final"][1] * 1e-3) / 1e12,
-                    "kernel": "gemm_kernel (tcgen05, all %d layers)" % (cfg["hidden"] + 1),
+                    "kernel": "gemm_kernel (tcgen05, all %d layers%s)" % (
+                        cfg["hidden"] + 1, "; both passes plus selection / gather / scatter" if refine else ""),
                     "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); only the "
                                    "reference's FLOPs count, the extra MMAs of a split mode do not"
                                    % peaks["src"],
@@ -372,6 +386,8 @@ def measure_batch(env, cfg, precision, n_utts, steps, warmup, sample_clocks):
         "gpu_launches": int(sum(v[0] for v in prof.values())),
         "clocks": clocks, "checksum": checksum,
     }
+    if refine:
+        res["refine"] = refine
     return res, am, batch
 
 
@@ -453,6 +469,7 @@ def run_gpu_arm(args, cfg):
             "roofline": main["roofline"],
             "roofline_frontend": main["roofline_frontend"],
             "kernel_ms_per_step": main["kernel_ms_per_step"],
+            "refine": main.get("refine"),
             "cpu_baseline": cpu,
             "e2e": e2e,
             "e2e_decode": e2e_decode,
@@ -730,8 +747,8 @@ def measure_other_modes(env, cfg, ref_pack, skip):
     """Throughput + parity of the other GEMM precisions on a 512-utterance batch (same net)."""
     import pocketkaldi_b200 as pk
     ctx = env.ctx
-    names = ["bf16", "fp16", "bf16x3"] + [k for k, a in (("fp16x3", "PREC_FP16X3"), ("fp16c8", "PREC_FP16C8"))
-                                           if hasattr(pk, a)]
+    names = ["bf16", "fp16", "bf16x3"] + [k for k, a in (("fp16x3", "PREC_FP16X3"), ("fp16c8", "PREC_FP16C8"),
+                                                          ("fp16r", "PREC_FP16R")) if hasattr(pk, a)]
     out = {}
     layers = make_layers(cfg)
     prior = uniform_prior(cfg)
@@ -851,7 +868,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="3", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default=DEFAULT_PRECISION,
-                    choices=["bf16", "bf16x3", "fp16", "fp16x3", "fp16c8"])
+                    choices=["bf16", "bf16x3", "fp16", "fp16x3", "fp16c8", "fp16r"])
     ap.add_argument("--utts", type=int, default=0, help="utterances per GPU (default: the config's)")
     ap.add_argument("--e2e-chunk", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=2)

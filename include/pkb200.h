@@ -47,6 +47,12 @@ extern "C" {
                              operands at twice the MMA rate: 2 MMA-equivalents per product,
                              error ~2^-15. Meets the parity bar; the first layer (whose spliced
                              input view has a 40-byte row pitch in FP8) runs as FP16X3        */
+#define PKB_PREC_FP16R 5  /* FP16 with selective refinement (log-likelihood outputs): every frame is
+                             computed with one FP16 MMA per product (error ~1e-2 at most), and the
+                             frames whose two best pdfs lie within the refinement margin (default
+                             0.04, pkb_am_set_refine_margin) -- the only ones whose ranking that
+                             error can change -- are recomputed with the FP16C8 operands. Other
+                             outputs (pkb_nnet_propagate, streams) run as FP16C8              */
 
 /* ---- fixed front-end geometry (src/fbank.h:7-13, src/cmvn.h:10-11) -------- */
 #define PKB_FBANK_DIM 40
@@ -137,6 +143,9 @@ int pkb_am_create(pkb_ctx_t *ctx, int n_layers, const int32_t *layer_types,
                   const int32_t *tid2pdf, int n_tid2pdf, int precision, pkb_am_t **am);
 void pkb_am_destroy(pkb_am_t *am);
 int pkb_am_num_pdfs(const pkb_am_t *am);        /* AcousticModel::num_pdfs, src/am.h:38 */
+/* PKB_PREC_FP16R: log-likelihood distance between a frame's two best pdfs below which the frame is
+ * recomputed with the FP16C8 operands (>= 0; 0 refines exact ties only). */
+int pkb_am_set_refine_margin(pkb_am_t *am, float margin);
 int pkb_am_input_dim(const pkb_am_t *am);       /* nnet input dim = (L+R+1) * feat dim  */
 int pkb_am_left_context(const pkb_am_t *am);
 int pkb_am_right_context(const pkb_am_t *am);
@@ -238,6 +247,9 @@ int pkb_batch_get_rows(pkb_batch_t *batch, int which, int64_t frame0, int64_t n_
  * pkb_loglik16_expand for a whole block). Needs a model that ends in a softmax.
  * Switching releases the buffer of the other form. */
 int pkb_batch_set_compact(pkb_batch_t *batch, int on);
+/* PKB_PREC_FP16R: GEMM rows of the latest pkb_batch_run (frames plus the context rows between
+ * utterances) and how many frames its second pass recomputed. Zeros for other precisions. */
+int pkb_batch_refine_stats(const pkb_batch_t *batch, int64_t *rows, int64_t *refined);
 /* Host-side expansion of a block of compact rows: out[t][p] = prob_scale * (half(h[t][p]) + off[t]).
  * Does not touch the GPU. */
 int pkb_loglik16_expand(const uint16_t *h, const float *off, int64_t n_frames, int num_pdfs,

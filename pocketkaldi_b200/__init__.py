@@ -31,6 +31,7 @@ from .binding import (  # noqa: F401
     PREC_FP16,
     PREC_FP16X3,
     PREC_FP16C8,
+    PREC_FP16R,
     STAGE_FBANK,
     STAGE_CMVN,
     STAGE_NNET,

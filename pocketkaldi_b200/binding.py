@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libpkb200.so")
 CSRC = os.path.join(HERE, "csrc")
 
 PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2
-PREC_FP16X3, PREC_FP16C8 = 3, 4
+PREC_FP16X3, PREC_FP16C8, PREC_FP16R = 3, 4, 5
 STAGE_FBANK, STAGE_CMVN, STAGE_NNET, STAGE_ALL = 1, 2, 4, 7
 STAGE_NO_FEATS = 8  # with STAGE_CMVN + a model: skip the FP32 copy of the CMVN features
 BUF_PCM, BUF_RAW, BUF_FEATS, BUF_LOGLIK = 0, 1, 2, 3
@@ -68,6 +68,7 @@ _SIGNATURES = [
                                 C.POINTER(_VP)]),
     ("pkb_am_destroy", None, [_VP]),
     ("pkb_am_num_pdfs", C.c_int, [_VP]),
+    ("pkb_am_set_refine_margin", C.c_int, [_VP, C.c_float]),
     ("pkb_am_input_dim", C.c_int, [_VP]),
     ("pkb_am_left_context", C.c_int, [_VP]),
     ("pkb_am_right_context", C.c_int, [_VP]),
@@ -95,6 +96,7 @@ _SIGNATURES = [
     ("pkb_batch_get_rows", C.c_int, [_VP, C.c_int, C.c_int64, C.c_int64, _VP]),
     ("pkb_batch_checksum", C.c_int, [_VP, C.c_int, C.POINTER(C.c_double)]),
     ("pkb_batch_set_compact", C.c_int, [_VP, C.c_int]),
+    ("pkb_batch_refine_stats", C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("pkb_fst_load", C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
     ("pkb_fst_create", C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, C.c_int, _VP, C.POINTER(_VP)]),
     ("pkb_fst_destroy", None, [_VP]),
@@ -431,6 +433,10 @@ class AcousticModel:
     def num_pdfs(self):
         return self.ctx.lib.pkb_am_num_pdfs(self.h)
 
+    def set_refine_margin(self, margin):
+        """PREC_FP16R: frames whose two best pdfs are closer than `margin` are recomputed."""
+        _check(self.ctx.lib.pkb_am_set_refine_margin(self.h, float(margin)))
+
     def input_dim(self):
         return self.ctx.lib.pkb_am_input_dim(self.h)
 
@@ -655,6 +661,12 @@ class Batch:
                                              nw.ctypes.data, wt.ctypes.data))
         hyps = [None if nw[u] < 0 else [int(x) for x in words[u, :min(int(nw[u]), max_words)]] for u in range(n)]
         return hyps, wt[:n].copy()
+
+    def refine_stats(self):
+        """(GEMM rows, frames recomputed) of the latest run under PREC_FP16R."""
+        rows, sel = C.c_int64(0), C.c_int64(0)
+        _check(self.ctx.lib.pkb_batch_refine_stats(self.h, C.byref(rows), C.byref(sel)))
+        return rows.value, sel.value
 
     def set_compact(self, on=True):
         """Half-size output of the nnet stage (see pkb_batch_set_compact in include/pkb200.h)."""

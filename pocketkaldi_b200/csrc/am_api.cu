@@ -282,6 +282,7 @@ struct pkb_batch {
   pkb::DevBuf loglik16, loglik_off;
   pkb::DevBuf vit_work, vit_out, vit_tid2pdf;  // GPU Viterbi: workspace, results, device tid2pdf
   Workspace ws;
+  pkb::Refine rf;
   pkb::PaddedPlanes planes;
   int64_t padded = 0, gemm_rows = 0;
   std::vector<int64_t> pad_off;  // host copy: first padded row of every utterance
@@ -347,6 +348,8 @@ void pkb_am_destroy(pkb_am_t *am) {
   for (auto &st : am->stages) {
     st.w_hi.release();
     st.w_lo.release();
+    st.w8_hi.release();
+    st.w8_lo.release();
     st.bias.release();
   }
   am->splice_stage.w_hi.release();
@@ -354,6 +357,7 @@ void pkb_am_destroy(pkb_am_t *am) {
   am->splice_stage.bias.release();
   am->log_prior.release();
   am->ws.release();
+  am->rf.release();
   am->meta.dev.release();
   am->in_f32.release();
   am->out_f32.release();
@@ -414,8 +418,8 @@ static int am_compute_device(pkb_ctx_t *c, pkb_am_t *am, const float *feats, con
   in.rows = rows;
   in.cols = (am->left + am->right + 1) * dp;
   in.pitch_elems = dp;
-  return pkb::nnet_forward(am, &ws, in, &am->splice_stage, pkb::kFinalLoglik, prob_scale,
-                           am->out_f32.as<float>());
+  return pkb::nnet_forward_refined(am, &ws, &am->rf, in, &am->splice_stage, ws.row_map.as<int32_t>(),
+                                   pkb::kFinalLoglik, prob_scale, am->out_f32.as<float>());
 }
 
 int pkb_am_compute(pkb_ctx_t *c, pkb_am_t *am, const float *feats, const int32_t *num_frames,
@@ -578,6 +582,7 @@ int pkb_batch_create(pkb_ctx_t *c, pkb_am_t *am, int n_utts, const int32_t *num_
       std::vector<int64_t> &pad_off = b->pad_off;
       pkb::padded_rows(m, am->left, am->right, &pad_off, &b->padded, &b->gemm_rows);
       Workspace &ws = b->ws;
+      ws.fast_only = am->refine != 0;  // the FP8 operand planes only exist for the refined rows
       if ((rc = pkb::workspace_ensure(am, &ws, b->gemm_rows)) != PKB_OK) break;
       const int dp = am->feat_dim_pad;
       const size_t plane_bytes = std::max<size_t>(16, static_cast<size_t>(b->padded) * dp * 2);
@@ -637,6 +642,7 @@ void pkb_batch_destroy(pkb_batch_t *b) {
   b->vit_tid2pdf.release();
   b->sum.release();
   b->ws.release();
+  b->rf.release();
   b->meta.dev.release();
   delete b;
 }
@@ -681,13 +687,29 @@ int pkb_batch_run(pkb_batch_t *b, int stages) {
     in.rows = b->gemm_rows;
     in.cols = (am->left + am->right + 1) * am->feat_dim_pad;
     in.pitch_elems = am->feat_dim_pad;
+    const int32_t *row_map = b->ws.row_map.as<int32_t>();
     if (b->compact)
-      PKB_TRY(pkb::nnet_forward(am, &b->ws, in, &am->splice_stage, pkb::kFinalCompact, b->prob_scale,
-                                nullptr, b->loglik16.as<uint16_t>(), b->loglik_off.as<float>()));
+      PKB_TRY(pkb::nnet_forward_refined(am, &b->ws, &b->rf, in, &am->splice_stage, row_map,
+                                        pkb::kFinalCompact, b->prob_scale, nullptr,
+                                        b->loglik16.as<uint16_t>(), b->loglik_off.as<float>()));
     else
-      PKB_TRY(pkb::nnet_forward(am, &b->ws, in, &am->splice_stage, pkb::kFinalLoglik, b->prob_scale,
-                                b->loglik.as<float>()));
+      PKB_TRY(pkb::nnet_forward_refined(am, &b->ws, &b->rf, in, &am->splice_stage, row_map,
+                                        pkb::kFinalLoglik, b->prob_scale, b->loglik.as<float>()));
   }
+  return PKB_OK;
+}
+
+int pkb_batch_refine_stats(const pkb_batch_t *b, int64_t *rows, int64_t *refined) {
+  PKB_REQUIRE(b, "pkb_batch_refine_stats: batch is NULL");
+  if (rows) *rows = b->rf.last_rows;
+  if (refined) *refined = b->rf.last_selected;
+  return PKB_OK;
+}
+
+int pkb_am_set_refine_margin(pkb_am_t *am, float margin) {
+  PKB_REQUIRE(am, "pkb_am_set_refine_margin: model is NULL");
+  PKB_REQUIRE(margin >= 0.0f && margin < 1.0e4f, "pkb_am_set_refine_margin: margin %g out of range", margin);
+  am->refine_margin = margin;
   return PKB_OK;
 }
 

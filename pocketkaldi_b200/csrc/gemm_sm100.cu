@@ -701,7 +701,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           ss += p.in_sumsq[static_cast<size_t>(row) * p.in_sumsq_tiles + i];
         rs = sqrtf(p.in_dim / ss);  // NormalizeLayer: no floor (src/nnet.cc:71-73)
       }
-      if (PLANES == 3) rs *= p.acc_scale;  // FP16C8 weights are stored times a power of two
+      rs *= p.acc_scale;  // FP16C8 weights are stored times a power of two (1 otherwise)
 
       long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tkm = 0;
       const bool dbg_on = kProbes && p.dbg != nullptr && warp == 4 && lane == 0;  // team 0
@@ -855,6 +855,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           float run_max = -INFINITY, run_sum = 0.0f;
           float run_mzl = -INFINITY;  // compact mode: max over columns of z - log_prior
           const bool compact = p.final_mode == 3;
+          // the per-row maximum of z - log_prior is exchanged for the compact output and for the
+          // near-tie count of the refinement pass (p.near_cnt)
+          const bool want_mzl = compact || p.near_cnt != nullptr;
 #pragma unroll 1
           for (int c = 0; c < kChunks; ++c) {
             const int col0 = n0 + cbase + c * 32;
@@ -880,7 +883,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             float cmax = z[0];
 #pragma unroll
             for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, z[i]);
-            if (compact) {
+            if (want_mzl) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 lp = *reinterpret_cast<const float4 *>(s_lp + cbase + c * 32 + i);
@@ -906,7 +909,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                               team * (kHalves - 1) * kBlockM;
           if (chalf != 0) {
             s_half[(chalf - 1) * kBlockM + rit] = make_float2(run_max, run_sum);
-            if (compact) s_half_mzl[(chalf - 1) * kBlockM + rit] = run_mzl;
+            if (want_mzl) s_half_mzl[(chalf - 1) * kBlockM + rit] = run_mzl;
           }
           if (dbg_on) tk2 = clock64();
           named_bar_sync(1 + team, kTeamThreads);
@@ -921,7 +924,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               nm = m2;
             }
             __stcg(&xbase[n_blk * kBlockM + rit], make_float2(nm, sm));
-            if (compact) {
+            if (want_mzl) {
               float mz = run_mzl;
 #pragma unroll
               for (int h = 0; h < kHalves - 1; ++h) mz = fmaxf(mz, s_half_mzl[h * kBlockM + rit]);
@@ -958,14 +961,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               mx = nm;
             }
             lse = mx + logf(ssum);
-            if (compact) {
+            if (want_mzl) {
               const float *zbase = p.mzl_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
               float mz = -INFINITY;
               for (int j = 0; j < p.n_tiles_n; ++j) mz = fmaxf(mz, __ldcg(&zbase[j * kBlockM + rit]));
               // reference point of this frame's 16-bit values: the largest max(z - lse, floor) - lp
               // unless the floor binds (softmax below 1e-20), which only moves the point
               off16 = mz - lse;
-              if (n_blk == 0 && chalf == 0 && row_ok) p.out_off[row] = off16;
+              if (compact && n_blk == 0 && chalf == 0 && row_ok) p.out_off[row] = off16;
             }
           }
         }
@@ -979,6 +982,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         if (p.final_mode == 3) {
           // compact: two 32-column chunks fill one 128-byte staging row of halves
           const bool vec16_ok = (p.ld_f32 & 7) == 0;
+          const bool count_near = p.near_cnt != nullptr;
+          const __half2 near2 = __float2half2_rn(-p.near_margin);
+          __half2 cnt2 = __float2half2_rn(0.0f);  // <= 128 columns per thread: exact in FP16
 #pragma unroll 1
           for (int c = 0; c < kChunks; c += 2) {
             const int col0 = n0 + cbase + c * 32;
@@ -999,6 +1005,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 const float t3 = fmaxf(fmaf(__uint_as_float(v[i + 3]), rs, b.w) - lse, floor_v) - lp.w - off16;
                 hbits[hc * 16 + i / 2] = pack_f16(t0, t1);
                 hbits[hc * 16 + i / 2 + 1] = pack_f16(t2, t3);
+              }
+            }
+            if (count_near) {
+              // columns within near_margin of this frame's best one: the stored value is the
+              // distance from it. Padding columns (zero weights) are masked by their index.
+              if (col0 + 64 <= p.N_valid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  cnt2 = __hadd2(cnt2, __hgt2(*reinterpret_cast<const __half2 *>(&hbits[i]), near2));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const __half2 g = __hgt2(*reinterpret_cast<const __half2 *>(&hbits[i]), near2);
+                  const __half zero = __float2half(0.0f);
+                  cnt2 = __hadd2(cnt2, __halves2half2(col0 + 2 * i < p.N_valid ? __low2half(g) : zero,
+                                                      col0 + 2 * i + 1 < p.N_valid ? __high2half(g) : zero));
+                }
               }
             }
             if (vec16_ok) {
@@ -1022,7 +1045,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                   dst[i] = static_cast<uint16_t>((i & 1) ? (hbits[i >> 1] >> 16) : (hbits[i >> 1] & 0xffffu));
             }
           }
+          if (count_near && row_ok) {
+            const int n = static_cast<int>(__low2float(cnt2) + __high2float(cnt2));
+            if (n > 0) atomicAdd(p.near_cnt + row, n);
+          }
         } else {
+        const bool count_near = p.near_cnt != nullptr && p.final_mode == 2;
+        const float near_thr = off16 - p.near_margin;
+        int near_n = 0;
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c) {
           const int col0 = n0 + cbase + c * 32;
@@ -1052,11 +1082,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 lp = *reinterpret_cast<const float4 *>(s_lp + cbase + c * 32 + i);
-              z[i + 0] = (fmaxf(z[i + 0] - lse, floor_v) - lp.x) * sc;
-              z[i + 1] = (fmaxf(z[i + 1] - lse, floor_v) - lp.y) * sc;
-              z[i + 2] = (fmaxf(z[i + 2] - lse, floor_v) - lp.z) * sc;
-              z[i + 3] = (fmaxf(z[i + 3] - lse, floor_v) - lp.w) * sc;
+              z[i + 0] = fmaxf(z[i + 0] - lse, floor_v) - lp.x;
+              z[i + 1] = fmaxf(z[i + 1] - lse, floor_v) - lp.y;
+              z[i + 2] = fmaxf(z[i + 2] - lse, floor_v) - lp.z;
+              z[i + 3] = fmaxf(z[i + 3] - lse, floor_v) - lp.w;
             }
+            if (count_near) {
+              if (nvalid >= 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) near_n += z[i] > near_thr ? 1 : 0;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) near_n += (i < nvalid && z[i] > near_thr) ? 1 : 0;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) z[i] *= sc;
           }
           if (vec_ok) {
             if (dbg_on) q2 = clock64();
@@ -1088,6 +1129,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               if (i < nvalid) dst[i] = z[i];
           }
         }
+        if (count_near && row_ok && near_n > 0) atomicAdd(p.near_cnt + row, near_n);
         }
         tc_fence_before();
         __syncwarp();

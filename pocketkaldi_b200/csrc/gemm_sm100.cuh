@@ -60,7 +60,12 @@ struct GemmParams {
   int final_mode;
   uint16_t *out_h16;   // compact: [M][ld_f32] IEEE half bits (padded-row layout like out_f32)
   float *out_off;      // compact: [M]
-  float *mzl_part;     // compact: [M][n_tiles_n] per-tile max(z - log_prior), exchanged like lse_part
+  float *mzl_part;     // compact / near_cnt: [M][n_tiles_n] per-tile max(z - log_prior), exchanged like lse_part
+  // refinement (final_mode 2 and 3): near_cnt[row] += number of columns whose log-likelihood lies
+  // within near_margin of the row's best one (the best column counts itself: >= 2 means a near-tie).
+  // Zeroed by the caller; nullptr switches the count off.
+  int *near_cnt;
+  float near_margin;
   float2 *lse_part;    // final softmax: [M][n_tiles_n] (max, sum exp) exchanged between column tiles
   int *tile_done;      // final softmax: [m_tiles] arrival counters (zeroed by the launcher)
   const float *log_prior;  // [N_pad]

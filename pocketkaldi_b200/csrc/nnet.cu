@@ -220,6 +220,20 @@ int pack_stage_c8(Ctx *c, Stage *st, const float *W, const float *b, int out_dim
 
 }  // namespace
 
+void Refine::release() {
+  near_cnt.release();
+  list.release();
+  n_sel.release();
+  in_hi.release();
+  in_lo.release();
+  out_f32.release();
+  out_h16.release();
+  out_off.release();
+  ws.release();
+  if (h_n_sel) cudaFreeHost(h_n_sel);
+  h_n_sel = nullptr;
+}
+
 void Workspace::release() {
   for (int i = 0; i < 2; ++i) {
     act_hi[i].release();
@@ -251,7 +265,7 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
              const float *prior, int num_pdfs, int left, int right, const int32_t *tid2pdf,
              int n_tid2pdf, int precision, pkb_am **out) {
   PKB_REQUIRE(c && out, "pkb_am_create: NULL argument");
-  PKB_REQUIRE(precision >= PKB_PREC_BF16 && precision <= PKB_PREC_FP16C8,
+  PKB_REQUIRE(precision >= PKB_PREC_BF16 && precision <= PKB_PREC_FP16R,
               "pkb_am_create: unknown precision %d", precision);
   PKB_REQUIRE(left >= 0 && right >= 0, "pkb_am_create: negative context");
   PKB_REQUIRE(n_layers > 0 && types, "pkb_am_create: empty layer list");
@@ -259,7 +273,11 @@ int am_build(Ctx *c, int n_layers, const int32_t *types, const float *const *wei
   pkb_am *am = new pkb_am();
   am->c = c;
   am->precision = precision;
-  am->c8 = precision == PKB_PREC_FP16C8 ? 1 : 0;
+  am->refine = precision == PKB_PREC_FP16R ? 1 : 0;
+  am->c8 = (precision == PKB_PREC_FP16C8 || am->refine) ? 1 : 0;
+  if (am->refine) {
+    if (const char *e = getenv("PKB_REFINE_MARGIN")) am->refine_margin = static_cast<float>(atof(e));
+  }
   am->planes = (precision == PKB_PREC_BF16X3 || precision == PKB_PREC_FP16X3 || am->c8) ? 2 : 1;
   am->fp16 = (precision == PKB_PREC_FP16 || precision == PKB_PREC_FP16X3 || am->c8) ? 1 : 0;
   am->left = left;
@@ -373,10 +391,10 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
   const int bufs = ns > 2 ? 2 : (ns > 1 ? 1 : 0);
   for (int i = 0; i < bufs; ++i) {
     PKB_TRY(ws->act_hi[i].ensure(static_cast<size_t>(rows) * max_hidden * 2));
-    if (am->c8) {
+    if (am->c8 && !ws->fast_only) {
       PKB_TRY(ws->act8_lo[i].ensure(static_cast<size_t>(rows) * max_hidden));
       PKB_TRY(ws->act8_hi[i].ensure(static_cast<size_t>(rows) * max_hidden));
-    } else if (am->planes == 2) {
+    } else if (am->planes == 2 && !am->c8) {
       PKB_TRY(ws->act_lo[i].ensure(static_cast<size_t>(rows) * max_hidden * 2));
     }
     PKB_TRY(ws->sumsq[i].ensure(static_cast<size_t>(rows) * max_tiles * 2 * sizeof(float)));
@@ -391,7 +409,8 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
 }
 
 int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *first,
-                 FinalMode mode_out, float prob_scale, float *d_out, uint16_t *d_h16, float *d_off) {
+                 FinalMode mode_out, float prob_scale, float *d_out, uint16_t *d_h16, float *d_off,
+                 bool fast, int *near_cnt, float near_margin) {
   Ctx *c = am->c;
   const int64_t rows = ws->rows;
   if (rows == 0) return PKB_OK;
@@ -418,8 +437,8 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
     const Stage &st = i == 0 ? *first : am->stages[i];
     const bool final = i + 1 == ns;
     // operand mode of this stage and the form its epilogue has to produce for the next one
-    const int mode = st.c8 ? 3 : am->planes;
-    const bool out8 = !final && am->c8;
+    const int mode = fast ? 1 : (st.c8 ? 3 : am->planes);
+    const bool out8 = !fast && !final && am->c8;
     CUtensorMap tm_a_hi, tm_a_lo, tm_a_x;
     PKB_TRY(make_tensor_map(&tm_a_hi, a_hi, a_cols, rows, static_cast<uint64_t>(a_pitch) * 2, kBlockM));
     if (mode == 2) {
@@ -451,7 +470,7 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
     if (!final) {
       const int buf = static_cast<int>(i & 1);
       p.out_hi = ws->act_hi[buf].as<__nv_bfloat16>();
-      p.out_lo = (am->planes == 2 && !am->c8) ? ws->act_lo[buf].as<__nv_bfloat16>() : nullptr;
+      p.out_lo = (!fast && am->planes == 2 && !am->c8) ? ws->act_lo[buf].as<__nv_bfloat16>() : nullptr;
       p.out8_lo = out8 ? ws->act8_lo[buf].as<uint8_t>() : nullptr;
       p.out8_hi = out8 ? ws->act8_hi[buf].as<uint8_t>() : nullptr;
       p.ld_out = st.n_pad;
@@ -465,7 +484,11 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
         PKB_REQUIRE(d_h16 && d_off, "nnet_forward: the compact output needs its two buffers");
         p.out_h16 = d_h16;
         p.out_off = d_off;
-        p.mzl_part = ws->mzl_part.as<float>();
+      }
+      p.mzl_part = ws->mzl_part.as<float>();
+      if (near_cnt != nullptr && (p.final_mode == 2 || p.final_mode == 3)) {
+        p.near_cnt = near_cnt;
+        p.near_margin = near_margin;
       }
       p.lse_part = ws->lse_part.as<float2>();
       p.tile_done = ws->tile_done.as<int>();
@@ -507,6 +530,164 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       in_sumsq_tiles = p.n_tiles_n * sumsq_parts(mode);
       in_dim = static_cast<float>(st.out_dim);
     }
+  }
+  return PKB_OK;
+}
+
+namespace {
+// Rows whose near-tie count reached 2, in row order inside a block of 1024 rows.
+__global__ void __launch_bounds__(1024) select_rows_kernel(const int *__restrict__ near_cnt,
+                                                           const int32_t *__restrict__ row_map,
+                                                           int64_t rows, int32_t *__restrict__ list,
+                                                           int *__restrict__ n_sel) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 1024 + threadIdx.x;
+  const bool sel = r < rows && near_cnt[r] >= 2 && (row_map == nullptr || row_map[r] >= 0);
+  const unsigned m = __ballot_sync(0xffffffffu, sel);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  if (warp == 0) {
+    const int v = s_warp[lane];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    s_warp[lane] = inc - v;
+    if (lane == 31) s_base = inc > 0 ? atomicAdd(n_sel, inc) : 0;
+  }
+  __syncthreads();
+  if (sel) list[s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u))] = static_cast<int32_t>(r);
+}
+
+// dst[i][0 .. v16) = src[list[i] * pitch16 .. + v16) in 16-byte units, for one or two planes.
+__global__ void gather_rows_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict__ lo,
+                                   const int32_t *__restrict__ list, int n, int v16, int pitch16,
+                                   uint4 *__restrict__ g_hi, uint4 *__restrict__ g_lo) {
+  const int64_t total = static_cast<int64_t>(n) * v16;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(g / v16), j = static_cast<int>(g % v16);
+    const int64_t src = static_cast<int64_t>(list[i]) * pitch16 + j;
+    g_hi[g] = hi[src];
+    if (lo != nullptr) g_lo[g] = lo[src];
+  }
+}
+
+// dst[list[i]][0 .. v) = src[i][0 .. v) in units of T.
+template <typename T>
+__global__ void scatter_rows_kernel(const T *__restrict__ src, const int32_t *__restrict__ list, int n,
+                                    int v, T *__restrict__ dst) {
+  const int64_t total = static_cast<int64_t>(n) * v;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(g / v), j = static_cast<int>(g % v);
+    dst[static_cast<int64_t>(list[i]) * v + j] = src[g];
+  }
+}
+
+int launch_scatter(Ctx *c, const void *src, const int32_t *list, int n, size_t row_bytes, void *dst) {
+  const int grid_cap = c->sm_count * 16;
+  LaunchScope scope(c, PKB_KERNEL_MISC);
+  if (row_bytes % 16 == 0) {
+    const int v = static_cast<int>(row_bytes / 16);
+    const int grid = static_cast<int>(std::min<int64_t>((static_cast<int64_t>(n) * v + 255) / 256, grid_cap));
+    scatter_rows_kernel<uint4><<<grid, 256, 0, c->stream>>>(static_cast<const uint4 *>(src), list, n, v,
+                                                            static_cast<uint4 *>(dst));
+  } else if (row_bytes % 4 == 0) {
+    const int v = static_cast<int>(row_bytes / 4);
+    const int grid = static_cast<int>(std::min<int64_t>((static_cast<int64_t>(n) * v + 255) / 256, grid_cap));
+    scatter_rows_kernel<uint32_t><<<grid, 256, 0, c->stream>>>(static_cast<const uint32_t *>(src), list, n, v,
+                                                               static_cast<uint32_t *>(dst));
+  } else {
+    const int v = static_cast<int>(row_bytes / 2);
+    const int grid = static_cast<int>(std::min<int64_t>((static_cast<int64_t>(n) * v + 255) / 256, grid_cap));
+    scatter_rows_kernel<uint16_t><<<grid, 256, 0, c->stream>>>(static_cast<const uint16_t *>(src), list, n, v,
+                                                               static_cast<uint16_t *>(dst));
+  }
+  PKB_CUDA(cudaGetLastError());
+  return PKB_OK;
+}
+}  // namespace
+
+int nnet_forward_refined(pkb_am *am, Workspace *ws, Refine *rf, const InputView &in,
+                         const Stage *first, const int32_t *row_map, FinalMode mode,
+                         float prob_scale, float *d_out, uint16_t *d_h16, float *d_off) {
+  if (!am->refine || (mode != kFinalLoglik && mode != kFinalCompact))
+    return nnet_forward(am, ws, in, first, mode, prob_scale, d_out, d_h16, d_off);
+  Ctx *c = am->c;
+  const int64_t rows = ws->rows;
+  rf->last_rows = rows;
+  rf->last_selected = 0;
+  if (rows == 0) return PKB_OK;
+  PKB_REQUIRE(in.cols % 8 == 0 && in.pitch_elems % 8 == 0,
+              "nnet_forward_refined: input rows must be multiples of 16 bytes");
+  PKB_TRY(rf->near_cnt.ensure(static_cast<size_t>(rows) * sizeof(int)));
+  PKB_TRY(rf->list.ensure(static_cast<size_t>(rows) * sizeof(int32_t)));
+  PKB_TRY(rf->n_sel.ensure(sizeof(int)));
+  if (rf->h_n_sel == nullptr)
+    PKB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&rf->h_n_sel), sizeof(int32_t), cudaHostAllocDefault));
+  PKB_CUDA(cudaMemsetAsync(rf->near_cnt.p, 0, static_cast<size_t>(rows) * sizeof(int), c->stream));
+  PKB_CUDA(cudaMemsetAsync(rf->n_sel.p, 0, sizeof(int), c->stream));
+  // pass 1: one FP16 MMA per product
+  PKB_TRY(nnet_forward(am, ws, in, first, mode, prob_scale, d_out, d_h16, d_off, true,
+                       rf->near_cnt.as<int>(), am->refine_margin));
+  {
+    LaunchScope scope(c, PKB_KERNEL_MISC);
+    select_rows_kernel<<<static_cast<unsigned>((rows + 1023) / 1024), 1024, 0, c->stream>>>(
+        rf->near_cnt.as<int>(), row_map, rows, rf->list.as<int32_t>(), rf->n_sel.as<int>());
+    PKB_CUDA(cudaGetLastError());
+  }
+  PKB_CUDA(cudaMemcpyAsync(rf->h_n_sel, rf->n_sel.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  PKB_CUDA(cudaStreamSynchronize(c->stream));
+  const int n = *rf->h_n_sel;
+  rf->last_selected = n;
+  if (n == 0) return PKB_OK;
+  // pass 2 over the selected rows: buffers grow with some headroom so that a slightly larger
+  // selection in the next batch does not reallocate
+  const size_t cap = static_cast<size_t>(n) + static_cast<size_t>(n) / 8 + 128;
+  const size_t in_bytes = static_cast<size_t>(in.cols) * 2;
+  const int out_dim = am->stages.back().out_dim;
+  if (rf->in_hi.cap < static_cast<size_t>(n) * in_bytes) {
+    PKB_TRY(rf->in_hi.ensure(cap * in_bytes));
+    PKB_TRY(rf->in_lo.ensure(cap * in_bytes));
+  }
+  if (mode == kFinalCompact) {
+    if (rf->out_h16.cap < static_cast<size_t>(n) * out_dim * 2) PKB_TRY(rf->out_h16.ensure(cap * out_dim * 2));
+    if (rf->out_off.cap < static_cast<size_t>(n) * sizeof(float)) PKB_TRY(rf->out_off.ensure(cap * sizeof(float)));
+  } else if (rf->out_f32.cap < static_cast<size_t>(n) * out_dim * sizeof(float)) {
+    PKB_TRY(rf->out_f32.ensure(cap * out_dim * sizeof(float)));
+  }
+  if (rf->ws.rows < n || rf->ws.act_hi[0].p == nullptr) {
+    PKB_TRY(workspace_ensure(am, &rf->ws, static_cast<int64_t>(cap)));
+  }
+  rf->ws.rows = n;
+  {
+    const int v16 = in.cols / 8, pitch16 = in.pitch_elems / 8;
+    const int grid = static_cast<int>(std::min<int64_t>((static_cast<int64_t>(n) * v16 + 255) / 256,
+                                                        static_cast<int64_t>(c->sm_count) * 16));
+    LaunchScope scope(c, PKB_KERNEL_MISC);
+    gather_rows_kernel<<<grid, 256, 0, c->stream>>>(
+        reinterpret_cast<const uint4 *>(in.hi), reinterpret_cast<const uint4 *>(in.lo),
+        rf->list.as<int32_t>(), n, v16, pitch16, rf->in_hi.as<uint4>(), rf->in_lo.as<uint4>());
+    PKB_CUDA(cudaGetLastError());
+  }
+  InputView in2;
+  in2.hi = rf->in_hi.as<__nv_bfloat16>();
+  in2.lo = rf->in_lo.as<__nv_bfloat16>();
+  in2.rows = n;
+  in2.cols = in.cols;
+  in2.pitch_elems = in.cols;
+  PKB_TRY(nnet_forward(am, &rf->ws, in2, first, mode, prob_scale, rf->out_f32.as<float>(),
+                       rf->out_h16.as<uint16_t>(), rf->out_off.as<float>()));
+  if (mode == kFinalCompact) {
+    PKB_TRY(launch_scatter(c, rf->out_h16.p, rf->list.as<int32_t>(), n, static_cast<size_t>(out_dim) * 2, d_h16));
+    PKB_TRY(launch_scatter(c, rf->out_off.p, rf->list.as<int32_t>(), n, sizeof(float), d_off));
+  } else {
+    PKB_TRY(launch_scatter(c, rf->out_f32.p, rf->list.as<int32_t>(), n, static_cast<size_t>(out_dim) * 4, d_out));
   }
   return PKB_OK;
 }

@@ -50,8 +50,20 @@ struct Workspace {
   int64_t rows = 0;  // M of every GEMM
   DevBuf act_hi[2], act_lo[2], sumsq[2], lse_part, mzl_part, tile_done, row_map;
   DevBuf act8_lo[2], act8_hi[2];  // FP16C8: E4M3 correction operands of the hidden activations
+  bool fast_only = false;         // only single-plane passes run on this workspace (FP16R first pass)
   // padded feature planes of the batch pipeline
   DevBuf feat_hi, feat_lo, pad_off;
+  void release();
+};
+
+// Scratch of the selective second pass of PKB_PREC_FP16R (nnet_forward_refined).
+struct Refine {
+  DevBuf near_cnt, list, n_sel;   // [rows] near-tie counts, selected rows, their number
+  DevBuf in_hi, in_lo;            // gathered (spliced) input rows of the selected frames
+  DevBuf out_f32, out_h16, out_off;
+  Workspace ws;
+  int32_t *h_n_sel = nullptr;     // pinned host copy of n_sel
+  int64_t last_rows = 0, last_selected = 0;  // of the latest forward pass (pkb_batch_refine_stats)
   void release();
 };
 
@@ -62,7 +74,11 @@ struct pkb_am {
   int precision = PKB_PREC_BF16;
   int planes = 1;  // 16-bit planes of the input features and of stage 0
   int fp16 = 0;    // operands are FP16 instead of BF16 (PKB_PREC_FP16, _FP16X3, _FP16C8)
-  int c8 = 0;      // PKB_PREC_FP16C8: stages after the first run in operand mode 3
+  int c8 = 0;      // PKB_PREC_FP16C8 / _FP16R: stages after the first run in operand mode 3
+  // PKB_PREC_FP16R: one FP16 MMA per product for every frame, then the frames whose two best
+  // pdfs lie within refine_margin of each other are recomputed with the FP16C8 operands
+  int refine = 0;
+  float refine_margin = 0.04f;
   int left = 0, right = 0, num_pdfs = 0;
   int input_dim = 0;   // nnet input dim
   int feat_dim = 0;    // input_dim / (left + right + 1) when divisible, else 0
@@ -79,6 +95,7 @@ struct pkb_am {
   std::vector<float> w0_host, b0_host;
   // scratch of the synchronous host-buffer entry points (pkb_am_compute, pkb_nnet_propagate)
   pkb::Workspace ws;
+  pkb::Refine rf;
   pkb::BatchMeta meta;
   pkb::DevBuf in_f32, out_f32;
 };
@@ -99,9 +116,23 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows);
 // utterances hold garbage; copy_rows_compact() removes them on the way out.
 // kFinalCompact writes d_h16 [ws->rows][out_dim] (IEEE half bits) and d_off [ws->rows] instead of
 // d_out; prob_scale is then left to the consumer.
+// fast: every stage as one 16-bit plane (the hi planes of whatever the model holds).
+// near_cnt (kFinalLoglik / kFinalCompact): see GemmParams::near_cnt.
 int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *first,
                  FinalMode mode, float prob_scale, float *d_out, uint16_t *d_h16 = nullptr,
-                 float *d_off = nullptr);
+                 float *d_off = nullptr, bool fast = false, int *near_cnt = nullptr,
+                 float near_margin = 0.0f);
+
+// nnet_forward for every precision; PKB_PREC_FP16R log-likelihoods take two passes:
+//   1. nnet_forward(fast) over all rows, counting per row the pdfs within am->refine_margin of
+//      the best one;
+//   2. the rows with a near-tie (count >= 2; row_map[row] >= 0 when a row map is given) are
+//      gathered, run through the FP16C8 stages and scattered over the first pass's output.
+// One host synchronisation in between (the number of selected rows sizes the second pass).
+int nnet_forward_refined(pkb_am *am, Workspace *ws, Refine *rf, const InputView &in,
+                         const Stage *first, const int32_t *row_map, FinalMode mode,
+                         float prob_scale, float *d_out, uint16_t *d_h16 = nullptr,
+                         float *d_off = nullptr);
 
 // Device (padded rows) -> host (compact frames) copy of frames [frame0, frame0 + n): one
 // cudaMemcpyAsync per utterance touched.

@@ -27,7 +27,7 @@ pkb_ctx_t *shim_ctx() {
   return ctx;
 }
 
-// GEMM arithmetic from PKB_PRECISION: "bf16", "fp16", "bf16x3", "fp16x3" or "fp16c8" (default:
+// GEMM arithmetic from PKB_PRECISION: "bf16", "fp16", "bf16x3", "fp16x3", "fp16c8" or "fp16r" (default:
 // bf16x3, a mode that meets the parity bar).
 int shim_precision() {
   const char *p = getenv("PKB_PRECISION");
@@ -35,6 +35,7 @@ int shim_precision() {
   if (p != nullptr && strcmp(p, "fp16") == 0) return PKB_PREC_FP16;
   if (p != nullptr && strcmp(p, "fp16x3") == 0) return PKB_PREC_FP16X3;
   if (p != nullptr && strcmp(p, "fp16c8") == 0) return PKB_PREC_FP16C8;
+  if (p != nullptr && strcmp(p, "fp16r") == 0) return PKB_PREC_FP16R;
   return PKB_PREC_BF16X3;
 }
 

@@ -21,7 +21,7 @@ LL_TOL = 2e-2
 ARGMAX_MIN = 0.999
 FEAT_TOL = 1e-4
 PRECISIONS = {"bf16": pk.PREC_BF16, "bf16x3": pk.PREC_BF16X3, "fp16": pk.PREC_FP16}
-PRECISIONS.update({k: getattr(pk, v) for k, v in (("fp16x3", "PREC_FP16X3"), ("fp16c8", "PREC_FP16C8"))
+PRECISIONS.update({k: getattr(pk, v) for k, v in (("fp16x3", "PREC_FP16X3"), ("fp16c8", "PREC_FP16C8"), ("fp16r", "PREC_FP16R"))
                    if hasattr(pk, v)})
 
 

@@ -38,7 +38,7 @@ METRIC = "acoustic frames/s (fbank+CMVN+nnet loglik)"
 # The precision the headline is quoted in. tests/test_gpu_baseline_nets.py asserts the
 # north_star parity bar for this mode on the config-3 and config-4 nets.
 DEFAULT_PRECISION = "fp16r"
-REFINE_MARGIN = float(os.environ.get("PKB_BENCH_REFINE_MARGIN", "0.04"))  # log-likelihood units; pkb_am_set_refine_margin
+REFINE_MARGIN = float(os.environ.get("PKB_BENCH_REFINE_MARGIN", "0.02"))  # log-likelihood units; pkb_am_set_refine_margin
 LL_TOL, ARGMAX_MIN, FEAT_TOL = 2e-2, 0.999, 1e-4
 SAMPLES_10S = 160000
 FRAMES_10S = 998

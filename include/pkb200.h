@@ -50,9 +50,11 @@ extern "C" {
 #define PKB_PREC_FP16R 5  /* FP16 with selective refinement (log-likelihood outputs): every frame is
                              computed with one FP16 MMA per product (error ~1e-2 at most), and the
                              frames whose two best pdfs lie within the refinement margin (default
-                             0.04, pkb_am_set_refine_margin) -- the only ones whose ranking that
-                             error can change -- are recomputed with the FP16C8 operands. Other
-                             outputs (pkb_nnet_propagate, streams) run as FP16C8              */
+                             0.02, pkb_am_set_refine_margin) -- the only ones whose ranking that
+                             error can change: the FP16 error differs by at most 7e-3 between the
+                             leading pdfs of a frame on the BASELINE nets, tools/
+                             refine_margin_stats.py -- are recomputed with the FP16C8 operands.
+                             Other outputs (pkb_nnet_propagate, streams) run as FP16C8        */
 
 /* ---- fixed front-end geometry (src/fbank.h:7-13, src/cmvn.h:10-11) -------- */
 #define PKB_FBANK_DIM 40

@@ -69,6 +69,13 @@ constexpr int num_threads(bool final, int planes) { return kMainThreads + 32 * e
 // bytes of epilogue staging per warp of a hidden stage: one 32 x 128-byte tile per 16-bit output
 // plane, or the FP16 tile plus two 32 x 64-byte FP8 tiles
 constexpr uint32_t hid_stage_bytes(int planes, bool out8) { return (out8 || planes == 2) ? 8192u : 4096u; }
+// Output stage epilogue: one row per lane, rows staged in shared memory and written by TMA bulk
+// tensor stores. An accumulator-fragment variant (tcgen05.ld 16x256b, four lanes writing 32
+// contiguous bytes of a row straight to global memory: no staging, no proxy fences, 64 KB more
+// shared memory for the operand ring) was measured on B200 and dropped: its stores are whole
+// sectors but four times as many L1->L2 write requests as full 128-byte lines, and pass 2 went
+// from 8.9k to 14.8k cycles per tile and team (output stage 43.5 -> 56.6 ms per config-3 step).
+constexpr uint32_t kFinalStageBytes = 16u * 4096u;
 constexpr int kMaxStages = 8;
 // clock64 probes of the pipeline phases (PKB_GEMM_DEBUG=1 prints them). Compiled in only with
 // -DPKB_GEMM_PROBES: even switched off at run time they cost the hidden stages cycles.
@@ -429,7 +436,7 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int planes, bool 
   // epilogue staging: one 32-row x 128-byte tile per warp (and per plane for BF16 outputs)
   // FINAL adds the CTA's fixed bias and log-prior column tiles (2 x block_n floats) and a 128-row (max, sum) scratch per team
   // (and per row one more float for the compact mode's max(z - log_prior))
-  L.epi_bytes = final ? 16 * 4096 + 2 * block_n * 4 + 3 * 128 * 8 + 3 * 128 * 4
+  L.epi_bytes = final ? kFinalStageBytes + 2 * block_n * 4 + 3 * 128 * 8 + 3 * 128 * 4
                       : epi_warps(false, planes) * hid_stage_bytes(planes, out8);
   uint32_t avail = kSmemBudget - 1024 /* alignment slack */ - 256 /* barriers */ - L.epi_bytes;
   L.stages = avail / L.stage_bytes;
@@ -673,7 +680,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     const uint32_t stg8_w = smem_u32(stg) + 4096 + lane * 64;
     const uint32_t stg_w = smem_u32(stg) + lane * 128;          // this lane's row
     // grouped schedule: this CTA's column tile never changes, keep its bias / log-prior in smem
-    float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + 16 * 4096);
+    float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + (FINAL ? kFinalStageBytes : 16u * 4096u));
     float *s_lp = s_bias + BN;
     constexpr int kEpiThreads = 32 * epi_warps(FINAL, PLANES);
     if (FINAL && p.group_sched) {
@@ -951,20 +958,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           }
           named_bar_sync(1 + team, kTeamThreads);
           if (dbg_on) tk3 = clock64();
-          // (3) combine the partials of this row (coalesced, independent loads)
+          // (3) combine the partials of this row: coalesced loads, four in flight
           {
-            float mx = -INFINITY, ssum = 0.0f;
-            for (int j = 0; j < p.n_tiles_n; ++j) {
-              const float2 e = __ldcg(&xbase[j * kBlockM + rit]);
-              const float nm = fmaxf(mx, e.x);
-              ssum = ssum * exp2f_fast((mx - nm) * kLog2e) + e.y * exp2f_fast((e.x - nm) * kLog2e);
-              mx = nm;
+            const float *zbase = p.mzl_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
+            float mx = -INFINITY, ssum = 0.0f, mz = -INFINITY;
+            for (int j0 = 0; j0 < p.n_tiles_n; j0 += 4) {
+              float2 e[4];
+              float zz[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const bool in = j0 + j < p.n_tiles_n;
+                e[j] = in ? __ldcg(&xbase[(j0 + j) * kBlockM + rit]) : make_float2(-INFINITY, 0.0f);
+                zz[j] = (in && want_mzl) ? __ldcg(&zbase[(j0 + j) * kBlockM + rit]) : -INFINITY;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float nm = fmaxf(mx, e[j].x);
+                ssum = ssum * exp2f_fast((mx - nm) * kLog2e) + e[j].y * exp2f_fast((e[j].x - nm) * kLog2e);
+                mx = nm;
+                mz = fmaxf(mz, zz[j]);
+              }
             }
             lse = mx + logf(ssum);
             if (want_mzl) {
-              const float *zbase = p.mzl_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
-              float mz = -INFINITY;
-              for (int j = 0; j < p.n_tiles_n; ++j) mz = fmaxf(mz, __ldcg(&zbase[j * kBlockM + rit]));
               // reference point of this frame's 16-bit values: the largest max(z - lse, floor) - lp
               // unless the floor binds (softmax below 1e-20), which only moves the point
               off16 = mz - lse;

@@ -78,7 +78,7 @@ struct pkb_am {
   // PKB_PREC_FP16R: one FP16 MMA per product for every frame, then the frames whose two best
   // pdfs lie within refine_margin of each other are recomputed with the FP16C8 operands
   int refine = 0;
-  float refine_margin = 0.04f;
+  float refine_margin = 0.02f;  // tools/refine_margin_stats.py: 3x the largest error spread seen
   int left = 0, right = 0, num_pdfs = 0;
   int input_dim = 0;   // nnet input dim
   int feat_dim = 0;    // input_dim / (left + right + 1) when divisible, else 0

@@ -62,10 +62,23 @@ constexpr int kMainThreads = 128;   // warps 0-3: TMA producer, MMA issuer, TMEM
 #endif
 // `planes` is the operand mode of the main loop: 1 = one 16-bit plane, 2 = hi + lo planes (three
 // MMAs per product), 3 = FP16 + FP8 corrections (two MMA-equivalents per product).
-constexpr int epi_teams(bool final, int planes) { return final ? PKB_FINAL_TEAMS : (planes == 1 ? PKB_HID_TEAMS : 1); }
-constexpr int team_warps(bool final, int planes) { return final ? 16 / PKB_FINAL_TEAMS : (planes == 2 ? 4 : PKB_HID_WARPS); }
-constexpr int epi_warps(bool final, int planes) { return epi_teams(final, planes) * team_warps(final, planes); }
-constexpr int num_threads(bool final, int planes) { return kMainThreads + 32 * epi_warps(final, planes); }
+// Accumulator stages in TMEM. The output stage's drain (two passes over the accumulator with the
+// cross-CTA softmax exchange in between, ~17k cycles) is twice as long as a single-plane MMA fill
+// (8k), so two 256-column stages leave that stage epilogue-bound. Four 128-column stages with one
+// epilogue team each were measured on B200 and are not used: a 128x128 tcgen05.mma of one CTA
+// reads 8 KB of shared memory per 64 cycles, exactly the 128 B/cycle the SM has, and the fill
+// slows down by more than the extra stages gain (output stage 38.8 -> 50.0 ms per config-3 step).
+constexpr int acc_stages(bool final, int bn) { return (void(final), void(bn), 2); }
+constexpr int epi_teams(bool final, int planes, int bn = 256) {
+  return (void(bn), final ? PKB_FINAL_TEAMS : (planes == 1 ? PKB_HID_TEAMS : 1));
+}
+constexpr int team_warps(bool final, int planes, int bn = 256) {
+  return final ? 16 / epi_teams(final, planes, bn) : (planes == 2 ? 4 : PKB_HID_WARPS);
+}
+constexpr int epi_warps(bool final, int planes, int bn = 256) {
+  return epi_teams(final, planes, bn) * team_warps(final, planes, bn);
+}
+constexpr int num_threads(bool final, int planes, int bn = 256) { return kMainThreads + 32 * epi_warps(final, planes, bn); }
 // bytes of epilogue staging per warp of a hidden stage: one 32 x 128-byte tile per 16-bit output
 // plane, or the FP16 tile plus two 32 x 64-byte FP8 tiles
 constexpr uint32_t hid_stage_bytes(int planes, bool out8) { return (out8 || planes == 2) ? 8192u : 4096u; }
@@ -381,17 +394,20 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
                : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_add(int *p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ int ld_relaxed(const int *p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ int ld_acquire(const int *p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
@@ -480,7 +496,7 @@ __device__ __forceinline__ bool get_tile(const GemmParams &p, int it, uint32_t r
 //   w_x = e4m3(W16 * 2^4); correction phase A = a_lo x w_x, phase B = a_x x w_lo, main = a_hi x w_hi.
 // OUT8 (hidden stages only): the epilogue writes the FP16C8 operand triple of the next stage.
 template <int BN, int PLANES, bool FINAL, int CG, bool OUT8>
-__global__ void __launch_bounds__(num_threads(FINAL, PLANES), 1)
+__global__ void __launch_bounds__(num_threads(FINAL, PLANES, BN), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
             const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_a_x,
@@ -493,9 +509,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
   uint64_t *full = bars;                       // [stages]
   uint64_t *empty = bars + kMaxStages;         // [stages]
-  uint64_t *tfull = bars + 2 * kMaxStages;     // [2]
-  uint64_t *tempty = bars + 2 * kMaxStages + 2;  // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 4);
+  constexpr int kAcc = acc_stages(FINAL, BN);  // accumulator stages of BN columns in TMEM
+  uint64_t *tfull = bars + 2 * kMaxStages;     // [kAcc <= 4]
+  uint64_t *tempty = bars + 2 * kMaxStages + 4;  // [kAcc <= 4]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t S = L.stages;
@@ -520,14 +537,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], CG * team_warps(FINAL, PLANES));  // both CTAs of a pair release the leader
+      mbar_init(&tempty[i], CG * team_warps(FINAL, PLANES, BN));  // both CTAs of a pair release the leader
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc<CG>(tmem_slot, 2 * BN);
+    tmem_alloc<CG>(tmem_slot, kAcc * BN);
     tmem_relinquish<CG>();
   }
   tc_fence_before();
@@ -597,7 +614,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       uint32_t s = 0, ph = 0;
       int m_blk, n_blk;
       for (int it = 0; get_tile<CG>(p, it, cta_rank, m_blk, n_blk); ++it) {
-        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        const uint32_t as = it % kAcc, aph = (it / kAcc) & 1;
         long long tw0 = 0, tw_full = 0;
         if (kProbes && p.dbg != nullptr) tw0 = clock64();
         mbar_wait<32>(&tempty[as], aph ^ 1);
@@ -665,12 +682,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     const int q = warp & 3;  // TMEM lane quadrant
     // FINAL: team = accumulator stage; inside a team two warps per lane quadrant, each owning
     // half of the tile's columns
-    constexpr int kTeams = epi_teams(FINAL, PLANES);
-    const int team = kTeams == 2 ? ((warp - 4) >> 3) : 0;
-    const int wt = kTeams == 2 ? ((warp - 4) & 7) : (warp - 4);
-    constexpr int kHalves = team_warps(FINAL, PLANES) / 4;  // warps per lane quadrant
+    constexpr int kTeams = epi_teams(FINAL, PLANES, BN);
+    constexpr int kTeamWarps = team_warps(FINAL, PLANES, BN);
+    const int team = (warp - 4) / kTeamWarps;
+    const int wt = (warp - 4) % kTeamWarps;
+    constexpr int kHalves = kTeamWarps / 4;  // warps per lane quadrant
     const int chalf = wt >> 2;
-    constexpr int kTeamThreads = 32 * team_warps(FINAL, PLANES);
+    constexpr int kTeamThreads = 32 * kTeamWarps;
     // per-warp staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7);
     // rows are written by their owner lane and read back 4 rows per instruction so that
     // every global store covers whole 128-byte lines
@@ -682,7 +700,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     // grouped schedule: this CTA's column tile never changes, keep its bias / log-prior in smem
     float *s_bias = reinterpret_cast<float *>(smem + L.epi_off + (FINAL ? kFinalStageBytes : 16u * 4096u));
     float *s_lp = s_bias + BN;
-    constexpr int kEpiThreads = 32 * epi_warps(FINAL, PLANES);
+    constexpr int kEpiThreads = 32 * epi_warps(FINAL, PLANES, BN);
     if (FINAL && p.group_sched) {
       const int nb = (static_cast<int>(blockIdx.x) / CG) % p.n_tiles_n;
       for (int i = threadIdx.x - kMainThreads; i < BN; i += kEpiThreads) {
@@ -694,7 +712,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     const int t_row = lane >> 3, t_chunk = lane & 7;            // transposed read role
     int m_blk, n_blk;
     for (int it = team; get_tile<CG>(p, it, cta_rank, m_blk, n_blk); it += kTeams) {
-      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const uint32_t as = it % kAcc, aph = (it / kAcc) & 1;
       const int m0 = m_blk * kBlockM;
       const int n0 = n_blk * BN;
       const int wrow0 = m0 + q * 32;  // first row of this warp
@@ -852,9 +870,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         // ---- pass 1 (softmax only): per-row (max, sum exp) over this warp's half of the
         //      tile's columns, exchanged with the warps / CTAs that own the other columns
         constexpr int kChunks = BN / 32 / kHalves;  // 32-column chunks per epilogue warp
-#if PKB_FINAL_TEAMS == 2
         static_assert(kChunks % 2 == 0, "the compact output packs two 32-column chunks per staging row");
-#endif
         const int cbase = chalf * (BN / kHalves);
         const float kLog2e = 1.4426950408889634f;
         float lse = 0.0f, off16 = 0.0f;
@@ -919,8 +935,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             if (want_mzl) s_half_mzl[(chalf - 1) * kBlockM + rit] = run_mzl;
           }
           if (dbg_on) tk2 = clock64();
-          named_bar_sync(1 + team, kTeamThreads);
-          float2 *xbase = p.lse_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
+          if (kHalves > 1) named_bar_sync(4 + team, kTeamThreads);
+          unsigned long long *xbase =
+              reinterpret_cast<unsigned long long *>(p.lse_part) + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
+          uint32_t *zbase = reinterpret_cast<uint32_t *>(p.mzl_part) + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
           if (chalf == 0) {
             float nm = run_max, sm = run_sum;
 #pragma unroll
@@ -930,53 +948,60 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               sm = sm * exp2f_fast((nm - m2) * kLog2e) + o.y * exp2f_fast((o.x - m2) * kLog2e);
               nm = m2;
             }
-            __stcg(&xbase[n_blk * kBlockM + rit], make_float2(nm, sm));
+            // one 64-bit word per (row, column tile): max in the low half, sum in the high half.
+            // The buffer is pre-filled with 0xFF bytes by the launcher and an all-ones high half
+            // (a NaN no computation below produces: sums are canonicalised) means "not written
+            // yet" -- the data is its own ready flag, no counter, no release / acquire chain.
+            if (sm != sm) sm = __int_as_float(0x7fc00000);
+            st_relaxed_u64(xbase + n_blk * kBlockM + rit,
+                           static_cast<unsigned long long>(__float_as_uint(nm)) |
+                               (static_cast<unsigned long long>(__float_as_uint(sm)) << 32));
             if (want_mzl) {
               float mz = run_mzl;
 #pragma unroll
               for (int h = 0; h < kHalves - 1; ++h) mz = fmaxf(mz, s_half_mzl[h * kBlockM + rit]);
-              __stcg(&p.mzl_part[(static_cast<size_t>(m_blk) * p.n_tiles_n + n_blk) * kBlockM + rit], mz);
+              if (mz != mz) mz = __int_as_float(0x7fc00000);
+              st_relaxed_u32(zbase + n_blk * kBlockM + rit, __float_as_uint(mz));
             }
           }
-          named_bar_sync(1 + team, kTeamThreads);
-          // (2) one thread releases the CTA's partials device-wide (the named barrier orders the
-          //     other threads' stores before it), then waits for the peer CTAs of this row block:
-          //     relaxed polling, one acquire at the end
-          if (wt == 0 && lane == 0) {
-            red_release_add(p.tile_done + m_blk, 1);
-            const long long t0 = clock64();
-            while (ld_relaxed(p.tile_done + m_blk) < p.n_tiles_n) {
-              // A peer that never arrives (it cannot with a co-resident grid) must not hang the
-              // device, and a trap would poison the whole context: give up after ~20 s of
-              // cycles, leave an error code for the host (check_device_error) and carry on.
-              if (clock64() - t0 > 40000000000ll) {
-                if (p.err_flag != nullptr) *reinterpret_cast<volatile int *>(p.err_flag) = 1;
-                break;
-              }
-            }
-            (void)ld_acquire(p.tile_done + m_blk);
-          }
-          named_bar_sync(1 + team, kTeamThreads);
+          // the scratch planes may be rewritten for this team's next tile only after they were read
+          if (kHalves > 1) named_bar_sync(4 + team, kTeamThreads);
           if (dbg_on) tk3 = clock64();
-          // (3) combine the partials of this row: coalesced loads, four in flight
+          // (2) every lane collects the partials of its own row from the peer CTAs of this row
+          //     block, eight loads in flight, polling until each word has been written
           {
-            const float *zbase = p.mzl_part + static_cast<size_t>(m_blk) * p.n_tiles_n * kBlockM;
             float mx = -INFINITY, ssum = 0.0f, mz = -INFINITY;
-            for (int j0 = 0; j0 < p.n_tiles_n; j0 += 4) {
-              float2 e[4];
-              float zz[4];
+            const long long t0 = clock64();
+            for (int j0 = 0; j0 < p.n_tiles_n; j0 += 8) {
+              unsigned long long w[8];
+              uint32_t zz[8];
+              while (true) {
+                bool ready = true;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const bool in = j0 + j < p.n_tiles_n;
-                e[j] = in ? __ldcg(&xbase[(j0 + j) * kBlockM + rit]) : make_float2(-INFINITY, 0.0f);
-                zz[j] = (in && want_mzl) ? __ldcg(&zbase[(j0 + j) * kBlockM + rit]) : -INFINITY;
+                for (int j = 0; j < 8; ++j) {
+                  const bool in = j0 + j < p.n_tiles_n;
+                  w[j] = in ? ld_relaxed_u64(xbase + (j0 + j) * kBlockM + rit) : 0xff800000ull;  // (-inf, 0)
+                  zz[j] = (in && want_mzl) ? ld_relaxed_u32(zbase + (j0 + j) * kBlockM + rit) : 0xff800000u;
+                  ready = ready && static_cast<uint32_t>(w[j] >> 32) != 0xffffffffu && zz[j] != 0xffffffffu;
+                }
+                if (ready) break;
+                // A peer that never arrives (it cannot with a co-resident grid) must not hang the
+                // device, and a trap would poison the whole context: give up after ~20 s of
+                // cycles, leave an error code for the host (check_device_error) and carry on.
+                if (clock64() - t0 > 40000000000ll) {
+                  if (p.err_flag != nullptr) *reinterpret_cast<volatile int *>(p.err_flag) = 1;
+                  break;
+                }
+                __nanosleep(100);
               }
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float nm = fmaxf(mx, e[j].x);
-                ssum = ssum * exp2f_fast((mx - nm) * kLog2e) + e[j].y * exp2f_fast((e[j].x - nm) * kLog2e);
+              for (int j = 0; j < 8; ++j) {
+                const float ex = __uint_as_float(static_cast<uint32_t>(w[j]));
+                const float ey = __uint_as_float(static_cast<uint32_t>(w[j] >> 32));
+                const float nm = fmaxf(mx, ex);
+                ssum = ssum * exp2f_fast((mx - nm) * kLog2e) + ey * exp2f_fast((ex - nm) * kLog2e);
                 mx = nm;
-                mz = fmaxf(mz, zz[j]);
+                mz = fmaxf(mz, __uint_as_float(zz[j]));
               }
             }
             lse = mx + logf(ssum);
@@ -1172,7 +1197,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<CG>(tmem_base, 2 * BN);
+    tmem_dealloc<CG>(tmem_base, kAcc * BN);
   }
 }
 
@@ -1240,16 +1265,20 @@ int launch_one(Ctx *c, const GemmMaps &mp, const GemmParams &p) {
     // the column tiles of a row block exchange softmax partials through global memory and wait
     // for each other: a cooperative launch guarantees that all CTAs are co-resident
     // (+1: a CTA pair may work on one row block past the end of the matrix)
-    PKB_CUDA(cudaMemsetAsync(p.tile_done, 0, sizeof(int) * ((p.M + kBlockM - 1) / kBlockM + 1), c->stream));
+    // exchange buffers: all-ones words mean "not written yet" (see the epilogue)
+    const size_t words = (static_cast<size_t>((p.M + kBlockM - 1) / kBlockM) + 1) * p.n_tiles_n * kBlockM;
+    PKB_CUDA(cudaMemsetAsync(p.lse_part, 0xFF, words * sizeof(float2), c->stream));
+    if (p.final_mode == 3 || p.near_cnt != nullptr)
+      PKB_CUDA(cudaMemsetAsync(p.mzl_part, 0xFF, words * sizeof(float), c->stream));
     CUtensorMap m0 = *a_hi, m1 = *a_lo, m2 = *w_hi, m3 = *w_lo, m5 = *a_x, m6 = *w_x;
     void *args[] = {&m0, &m1, &m2, &m3, &out_map, &m5, &m6, &pp};
     if (CG == 1) {
       PKB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid),
-                                           dim3(num_threads(FINAL, PLANES)), args, L.total, c->stream));
+                                           dim3(num_threads(FINAL, PLANES, BN)), args, L.total, c->stream));
     } else {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(num_threads(FINAL, PLANES));
+      cfg.blockDim = dim3(num_threads(FINAL, PLANES, BN));
       cfg.dynamicSmemBytes = L.total;
       cfg.stream = c->stream;
       cudaLaunchAttribute attr[2];
@@ -1273,7 +1302,7 @@ int launch_one(Ctx *c, const GemmMaps &mp, const GemmParams &p) {
   } else if (CG == 2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(num_threads(FINAL, PLANES));
+    cfg.blockDim = dim3(num_threads(FINAL, PLANES, BN));
     cfg.dynamicSmemBytes = L.total;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
@@ -1285,7 +1314,7 @@ int launch_one(Ctx *c, const GemmMaps &mp, const GemmParams &p) {
     cfg.numAttrs = 1;
     PKB_CUDA(cudaLaunchKernelEx(&cfg, kern, *a_hi, *a_lo, *w_hi, *w_lo, out_map, *a_x, *w_x, pp));
   } else {
-    kern<<<grid, num_threads(FINAL, PLANES), L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, out_map, *a_x,
+    kern<<<grid, num_threads(FINAL, PLANES, BN), L.total, c->stream>>>(*a_hi, *a_lo, *w_hi, *w_lo, out_map, *a_x,
                                                                    *w_x, pp);
   }
   PKB_CUDA(cudaGetLastError());

@@ -66,8 +66,8 @@ struct GemmParams {
   // Zeroed by the caller; nullptr switches the count off.
   int *near_cnt;
   float near_margin;
-  float2 *lse_part;    // final softmax: [M][n_tiles_n] (max, sum exp) exchanged between column tiles
-  int *tile_done;      // final softmax: [m_tiles] arrival counters (zeroed by the launcher)
+  float2 *lse_part;    // final softmax: [m_tiles + 1][n_tiles_n][128] (max, sum exp) exchanged between the
+                       // column tiles; filled with 0xFF bytes (= not written yet) by the launcher
   const float *log_prior;  // [N_pad]
   float scale, log_floor;
   int *err_flag;       // set by the launcher: mapped host word for "gave up waiting" reports

@@ -244,7 +244,6 @@ void Workspace::release() {
   }
   lse_part.release();
   mzl_part.release();
-  tile_done.release();
   row_map.release();
   feat_hi.release();
   feat_lo.release();
@@ -400,11 +399,11 @@ int workspace_ensure(pkb_am *am, Workspace *ws, int64_t rows) {
     PKB_TRY(ws->sumsq[i].ensure(static_cast<size_t>(rows) * max_tiles * 2 * sizeof(float)));
   }
   const Stage &last = am->stages.back();
-  PKB_TRY(ws->lse_part.ensure(static_cast<size_t>((rows + kBlockM - 1) / kBlockM) * kBlockM *
-                              2 * (last.n_pad / last.block_n) * sizeof(float2)));
-  PKB_TRY(ws->mzl_part.ensure(static_cast<size_t>((rows + kBlockM - 1) / kBlockM) * kBlockM *
-                              2 * (last.n_pad / last.block_n) * sizeof(float)));
-  PKB_TRY(ws->tile_done.ensure(sizeof(int) * (static_cast<size_t>((rows + kBlockM - 1) / kBlockM) + 1)));
+  // softmax exchange: one word per row and column tile (128-column tiles at most), one row block
+  // more than the matrix has (a CTA pair may work one block past the end)
+  const size_t words = (static_cast<size_t>((rows + kBlockM - 1) / kBlockM) + 1) * kBlockM * (last.n_pad / 128);
+  PKB_TRY(ws->lse_part.ensure(words * sizeof(float2)));
+  PKB_TRY(ws->mzl_part.ensure(words * sizeof(float)));
   return PKB_OK;
 }
 
@@ -451,9 +450,10 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       tm_a_lo = tm_a_hi;
       tm_a_x = tm_a_hi;
     }
+    const int block_n = st.block_n;
     GemmParams p{};
     p.M = static_cast<int>(rows);
-    p.n_tiles_n = st.n_pad / st.block_n;
+    p.n_tiles_n = st.n_pad / block_n;
     const int64_t tiles = static_cast<int64_t>(m_tiles) * p.n_tiles_n;
     PKB_REQUIRE(tiles <= INT32_MAX, "nnet_forward: too many tiles");
     p.num_tiles = static_cast<int>(tiles);
@@ -491,7 +491,6 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
         p.near_margin = near_margin;
       }
       p.lse_part = ws->lse_part.as<float2>();
-      p.tile_done = ws->tile_done.as<int>();
       p.log_prior = am->log_prior.as<float>();
       p.scale = prob_scale;
       p.log_floor = static_cast<float>(log(static_cast<double>(static_cast<float>(1.0e-20))));
@@ -503,7 +502,7 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
     static const bool no_pairs = getenv("PKB_GEMM_CG1") != nullptr;
     static const bool final_pairs = getenv("PKB_GEMM_FINAL_CG2") != nullptr;
     const bool want_pair = !final || mode >= 2 || final_pairs;
-    int cg = (want_pair && st.block_n == 256 && m_tiles >= 2 && !no_pairs) ? 2 : 1;
+    int cg = (want_pair && block_n == 256 && m_tiles >= 2 && !no_pairs) ? 2 : 1;
     // the grouped schedule of the softmax stage needs one CTA (pair) per column tile on the device
     if (final && p.final_mode != 0 && cg == 2 && (c->sm_count / 2) / p.n_tiles_n < 1) cg = 1;
     GemmMaps maps;
@@ -518,7 +517,7 @@ int nnet_forward(pkb_am *am, Workspace *ws, const InputView &in, const Stage *fi
       maps.w_lo = cg == 2 ? &st.tm_w_lo_half : &st.tm_w_lo;
       maps.w_x = maps.w_hi;
     }
-    PKB_TRY(launch_gemm(c, st.block_n, mode, final, cg, out8, maps, p));
+    PKB_TRY(launch_gemm(c, block_n, mode, final, cg, out8, maps, p));
     if (!final) {
       a_hi = p.out_hi;
       a_lo = p.out_lo;

@@ -48,7 +48,7 @@ struct InputView {
 // Per-batch scratch of the forward pass.
 struct Workspace {
   int64_t rows = 0;  // M of every GEMM
-  DevBuf act_hi[2], act_lo[2], sumsq[2], lse_part, mzl_part, tile_done, row_map;
+  DevBuf act_hi[2], act_lo[2], sumsq[2], lse_part, mzl_part, row_map;
   DevBuf act8_lo[2], act8_hi[2];  // FP16C8: E4M3 correction operands of the hidden activations
   bool fast_only = false;         // only single-plane passes run on this workspace (FP16R first pass)
   // padded feature planes of the batch pipeline

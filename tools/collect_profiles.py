@@ -24,7 +24,7 @@ def main():
         if os.path.exists(os.path.join(G, src)):
             json.dump(load(os.path.join(G, src)), open(os.path.join(P, dst), "w"))
     if os.path.exists(os.path.join(G, "decode_demo.txt")):
-        head = ("python tools/decode_demo.py --utts 128 --ref --precision fp16c8   (B200 box, 16 host cores; wall clock of the\n"
+        head = ("python tools/decode_demo.py --utts 128 --ref --precision fp16r   (B200 box, 16 host cores; wall clock of the\n"
                 "whole process: CUDA init, model load of the 85 MB config-3 net, list ingestion, acoustic scores, Viterbi, printing)\n"
                 "model: splice +-5 -> 6x1024 ReLU -> 3000 pdfs (random init), 40-word loop graph; 128 synthetic 10 s utterances\n\n")
         open(os.path.join(P, "r2_decode_demo.txt"), "w").write(head + open(os.path.join(G, "decode_demo.txt")).read())

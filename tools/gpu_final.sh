@@ -8,4 +8,4 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-sub > gpurun_out/ncu_launches.log 2>&1
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:'cmvn_kernel|fbank_kernel' -c 2 -o gpurun_out/r2_front python bench.py --utts 512 --steps 1 --warmup 0 --no-cpu --no-e2e --no-sub > gpurun_out/ncu_front.log 2>&1
 for c in 2 4 5; do timeout 300 python bench.py --config $c --no-cpu > gpurun_out/bench_config$c.json 2>/dev/null; done
-timeout 600 python tools/decode_demo.py --utts 128 --ref --precision fp16c8 > gpurun_out/decode_demo.txt 2>/dev/null
+timeout 600 python tools/decode_demo.py --utts 128 --ref --precision fp16r > gpurun_out/decode_demo.txt 2>/dev/null

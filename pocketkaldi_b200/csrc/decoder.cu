@@ -429,6 +429,7 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
   extern __shared__ __align__(16) char s_dense[];
   __shared__ int s_log, s_err, s_unres, s_changed;
   __shared__ unsigned long long s_min;
+  __shared__ unsigned int s_best;
   const int S = fst.num_states;
   uint32_t *cost[2], *warc[2];
   int *bp[2];
@@ -453,6 +454,13 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
     a_il[k] = ok ? __ldg(&fst.arc_il[a]) : 0;
     a_w[k] = ok ? __ldg(&fst.arc_w[a]) : 0.0f;
   }
+  // pdf of every emitting arc: the acoustic cost of the NEXT frame is loaded while the current one
+  // is searched (which pdfs an arc reads does not depend on the tokens), so the row's DRAM latency
+  // is off the critical path of the frame step
+  int a_pdf[kArcsPerThread];
+#pragma unroll
+  for (int k = 0; k < kArcsPerThread; ++k)
+    a_pdf[k] = (a_src[k] >= 0 && a_il[k] != 0) ? __ldg(&tid2pdf[a_il[k]]) : -1;
 
   // epsilon closure of frame table c under `cutoff`, winners, word back-pointers
   auto finish_frame = [&](int c, int p, double cutoff, const double (&td)[kArcsPerThread], const bool (&live)[kArcsPerThread]) {
@@ -531,6 +539,26 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
     __syncthreads();
   };
 
+  // Closes a frame: clears the previous table, reduces the best cost of the new one (the next
+  // frame's GetCutoff) and re-arms the two shared minima. Everyone is past a barrier on entry.
+  auto end_frame = [&](int c, int p) {
+    if (tid == 0) {
+      s_best = kInactive;
+      s_min = ~0ull;
+    }
+    __syncthreads();
+    uint32_t m = kInactive;
+    for (int s = tid; s < S; s += kVitThreads) {
+      cost[p][s] = kInactive;
+      warc[p][s] = kInactive;
+      m = min(m, cost[c][s]);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0 && m != kInactive) atomicMin(&s_best, m);
+    __syncthreads();
+  };
+
   for (int u = blockIdx.x; u < n_utts; u += gridDim.x) {
     const int T = num_frames[u];
     const float *ll0 = loglik + row_off[u] * num_pdfs;
@@ -551,29 +579,27 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
 #pragma unroll
       for (int k = 0; k < kArcsPerThread; ++k) { td[k] = 0.0; live[k] = false; }
       finish_frame(0, 1, INFINITY, td, live);
+      end_frame(0, 1);
     }
     bool alive = true;
+    float ac_next[kArcsPerThread];
+#pragma unroll
+    for (int k = 0; k < kArcsPerThread; ++k) ac_next[k] = (T > 0 && a_pdf[k] >= 0) ? __ldg(&ll0[a_pdf[k]]) : 0.0f;
     for (int f = 0; f < T && alive && !s_err; ++f) {
       const int prev = cur;
       cur ^= 1;
-      const float *ll = ll0 + static_cast<int64_t>(f) * num_pdfs;
-      // ---- GetCutoff below kBeamSize tokens
-      if (tid == 0) s_min = ~0ull;
-      __syncthreads();
+      float ac_cur[kArcsPerThread];
       {
-        uint32_t m = kInactive;
-        for (int s = tid; s < S; s += kVitThreads) m = min(m, cost[prev][s]);
+        const float *lln = ll0 + static_cast<int64_t>(f + 1) * num_pdfs;
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((tid & 31) == 0) atomicMin(&s_min, static_cast<unsigned long long>(m));
+        for (int k = 0; k < kArcsPerThread; ++k) {
+          ac_cur[k] = ac_next[k];
+          if (f + 1 < T && a_pdf[k] >= 0) ac_next[k] = __ldg(&lln[a_pdf[k]]);
+        }
       }
-      __syncthreads();
-      if (static_cast<uint32_t>(s_min) == kInactive) { alive = false; break; }
-      const float weight_cutoff =
-          static_cast<float>(static_cast<double>(unord32(static_cast<uint32_t>(s_min))) + static_cast<double>(beam));
-      __syncthreads();
-      if (tid == 0) s_min = ~0ull;
-      __syncthreads();
+      // ---- GetCutoff below kBeamSize tokens: the best cost was reduced when the table was finished
+      if (s_best == kInactive) { alive = false; break; }
+      const float weight_cutoff = static_cast<float>(static_cast<double>(unord32(s_best)) + static_cast<double>(beam));
       // ---- ProcessEmitting, pass 1: totals of this thread's arcs, bound on the next frame
       double td[kArcsPerThread];
       bool live[kArcsPerThread];
@@ -588,7 +614,7 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
           if (cs == kInactive) continue;
           const float c = unord32(cs);
           if (c > weight_cutoff) continue;
-          const float ac = -__ldg(&ll[__ldg(&tid2pdf[a_il[k]])]);
+          const float ac = -ac_cur[k];
           td[k] = static_cast<double>(c) + static_cast<double>(a_w[k]) + static_cast<double>(ac);
           live[k] = true;
           m = min(m, ord64(td[k]));
@@ -608,11 +634,7 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
       }
       __syncthreads();
       finish_frame(cur, prev, static_cast<double>(static_cast<float>(next_cutoff)), td, live);
-      for (int s = tid; s < S; s += kVitThreads) {
-        cost[prev][s] = kInactive;
-        warc[prev][s] = kInactive;
-      }
-      __syncthreads();
+      end_frame(cur, prev);
     }
 
     // ---- BestPath (src/decoder.cc:300-339)

@@ -68,6 +68,11 @@ constexpr int kMainThreads = 128;   // warps 0-3: TMA producer, MMA issuer, TMEM
 // epilogue team each were measured on B200 and are not used: a 128x128 tcgen05.mma of one CTA
 // reads 8 KB of shared memory per 64 cycles, exactly the 128 B/cycle the SM has, and the fill
 // slows down by more than the extra stages gain (output stage 38.8 -> 50.0 ms per config-3 step).
+// Releasing the stage after ONE pass (pass 1 also writes the logits through TMA stores, the warp
+// finishes its 32 x 128 block in place from L2 once the lse is known) was measured too: the MMA
+// warp no longer waits for TMEM, but the extra write + read + write of every output tile competes
+// with the operand loads (wait for shared-memory stages 3.7k -> 7.3k cycles per tile) and the
+// in-place finish takes as long as the pass it replaces (41.3 -> 45.5 ms, 43.3 ms with CTA pairs).
 constexpr int acc_stages(bool final, int bn) { return (void(final), void(bn), 2); }
 constexpr int epi_teams(bool final, int planes, int bn = 256) {
   return (void(bn), final ? PKB_FINAL_TEAMS : (planes == 1 ? PKB_HID_TEAMS : 1));

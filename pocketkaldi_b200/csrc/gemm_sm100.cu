@@ -509,8 +509,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   static_assert(!(FINAL && OUT8), "the output stage writes FP32 / compact rows");
   extern __shared__ uint8_t smem_raw[];
   const SmemLayout L = smem_layout(BN, PLANES, FINAL, CG, OUT8);
-  uint8_t *smem = reinterpret_cast<uint8_t *>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by pointer arithmetic on the shared array (not through an integer): the
+  // compiler keeps the address space and emits LDS / STS instead of generic loads and stores
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bar_off);
   uint64_t *full = bars;                       // [stages]
   uint64_t *empty = bars + kMaxStages;         // [stages]
@@ -709,7 +710,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (FINAL && p.group_sched) {
       const int nb = (static_cast<int>(blockIdx.x) / CG) % p.n_tiles_n;
       for (int i = threadIdx.x - kMainThreads; i < BN; i += kEpiThreads) {
-        s_bias[i] = p.bias[nb * BN + i];
+        // padding columns (zero weights) get a bias of -inf in the softmax modes: their logit is
+        // -inf, exp() == 0, without any per-element masking in pass 1; pass 2 never stores them
+        s_bias[i] = (p.final_mode != 0 && nb * BN + i >= p.N_valid) ? -INFINITY : p.bias[nb * BN + i];
         s_lp[i] = p.log_prior[nb * BN + i];
       }
       named_bar_sync(3, kEpiThreads);
@@ -902,11 +905,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
               z[i + 1] = fmaf(__uint_as_float(v[i + 1]), rs, b.y);
               z[i + 2] = fmaf(__uint_as_float(v[i + 2]), rs, b.z);
               z[i + 3] = fmaf(__uint_as_float(v[i + 3]), rs, b.w);
-            }
-            if (nvalid < 32) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i >= nvalid) z[i] = -INFINITY;  // padding columns: exp() == 0
             }
             float cmax = z[0];
 #pragma unroll

@@ -41,7 +41,7 @@ def main():
             w.writerow(["ID", "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum [ns]"])
             for r in rows[1:]:
                 w.writerow([r[h.index("ID")], r[ik], r[h.index("Grid Size")], r[h.index("Block Size")], r[iv]])
-        cls = {"fbank": 0.0, "cmvn": 0.0, "gemm hidden": 0.0, "gemm output": 0.0, "other": 0.0}
+        cls = {"fbank": 0.0, "cmvn": 0.0, "gemm hidden": 0.0, "gemm output": 0.0, "refine misc": 0.0, "other": 0.0}
         n = dict.fromkeys(cls, 0)
         for r in rows[1:]:
             k, t = r[ik], float(r[iv].replace(",", ""))
@@ -51,6 +51,8 @@ def main():
                 c = "cmvn"
             elif "gemm_kernel" in k:
                 c = "gemm output" if ", 1, " in k.split("gemm_kernel<")[1].split(">")[0] and k.split("gemm_kernel<")[1].split(",")[2].strip() == "1" else "gemm hidden"
+            elif "select_rows" in k or "gather_rows" in k or "scatter_rows" in k:
+                c = "refine misc"  # FP16R: selection, gather and scatter of the recomputed frames
             else:
                 c = "other"
             cls[c] += t
@@ -58,7 +60,8 @@ def main():
         tot = sum(v for k, v in cls.items() if k != "other")
         b = load(os.path.join(G, "bench_default.json"))
         km = b["kernel_ms_per_step"]
-        ev = {"fbank": km["fbank"], "cmvn": km["cmvn"], "gemm hidden": km["gemm"], "gemm output": km["gemm_final"], "other": km["misc"]}
+        ev = {"fbank": km["fbank"], "cmvn": km["cmvn"], "gemm hidden": km["gemm"], "gemm output": km["gemm_final"],
+              "refine misc": km["misc"], "other": 0.0}
         evt = sum(ev.values())
         with open(os.path.join(P, "r2_launch_shares.txt"), "w") as fd:
             fd.write("Share of the step per kernel class: ncu launch list (profiles/r2_launches.csv: cold cache, serialised,\n"
@@ -94,6 +97,39 @@ def main():
             for r in rows[2:]:
                 w.writerow([r[h.index(k)] for k in keep])
         print("front-end details:", len(rows) - 2, "kernels")
+    # ---- GEMM launches of one FP16R step (14 launches: FP16 pass + FP16C8 recompute), DRAM traffic
+    rep = os.path.join(G, "r2_gemm_fp16r.ncu-rep")
+    if os.path.exists(rep):
+        metrics = ("dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,"
+                   "sm__throughput.avg.pct_of_peak_sustained_elapsed,launch__grid_size,launch__registers_per_thread,"
+                   "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active")
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", metrics],
+                             stdout=subprocess.PIPE).stdout.decode()
+        open(os.path.join(P, "r2_ncu_gemm_fp16r.csv"), "w").write(raw)
+        rows = list(csv.reader(raw.splitlines()))
+        h, u = rows[0], rows[1]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tot = 0.0
+        for r in rows[2:]:
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r[h.index(k)].replace(",", "")) * scale[u[h.index(k)]]
+        frames = 510976  # 512 utterances x 998 frames
+        tp = os.path.join(P, "r2_gemm_traffic.json")
+        t = json.load(open(tp)) if os.path.exists(tp) else {}
+        t["config3_fp16r"] = {
+            "dram_bytes_per_frame": tot / frames,
+            "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum over the %d gemm_kernel launches of one "
+                      "step (FP16 pass + FP16C8 recompute of the near-tie frames) at 512 utterances (510976 frames), "
+                      "profiles/r2_ncu_gemm_fp16r.csv" % (len(rows) - 2),
+            "algorithmic_bytes_per_frame": 12160}
+        json.dump(t, open(tp, "w"), indent=1)
+        print("gemm traffic: %.0f B/frame over %d launches" % (tot / frames, len(rows) - 2))
+    for src, dst in (("bench_fp16c8.json", "r2_bench_fp16c8.json"),):
+        if os.path.exists(os.path.join(G, src)) and load(os.path.join(G, src)):
+            json.dump(load(os.path.join(G, src)), open(os.path.join(P, dst), "w"))
+    for src, dst in (("margin_stats.txt", "r2_refine_margin_stats.txt"), ("viterbi_bench.txt", "r2_viterbi_bench.txt")):
+        if os.path.exists(os.path.join(G, src)):
+            shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 
 
 if __name__ == "__main__":

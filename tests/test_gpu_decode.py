@@ -59,7 +59,7 @@ def test_words_identical_to_reference(wavs, toy_conf):
     if not os.path.exists(SHIM_CLI):
         pytest.skip("oracle/_ref/pocketkaldi_b200_cli not built (needs /root/reference at build time)")
     gold = golden_hyps()
-    for prec in ("bf16x3", "fp16c8", "fp16x3"):   # every mode that meets the parity bar
+    for prec in ("bf16x3", "fp16r", "fp16c8", "fp16x3"):   # every mode that meets the parity bar
         for name in ("hello", "cat"):
             (_, hyp, llpf), = run_cli(SHIM_CLI, toy_conf, wavs[name], {"PKB_PRECISION": prec})
             assert hyp == gold[name][0], (prec, name, hyp, gold[name][0])

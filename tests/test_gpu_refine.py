@@ -123,3 +123,27 @@ def test_margin_validation(ctx):
     with pytest.raises(pk.PkbError):
         am.set_refine_margin(-1.0)
     am.close()
+
+
+def test_streams_run_the_fp16c8_stages(ctx):
+    # a stream's GEMMs have a few hundred rows: no selection pass, the FP16R model simply runs
+    # its FP16C8 stages there, bit for bit what a FP16C8 model produces
+    rng = np.random.default_rng(21)
+    layers = formats.make_dnn(rng, 440, 256, 2, 600)
+    prior = np.full(600, 1.0 / 600, np.float32)
+    g = synth_global_cmvn()
+    from pocketkaldi_b200.synth import synth_pcm
+    S, chunk, n_chunks = 3, 2560, 6
+    pcm = synth_pcm(99, np.arange(S), chunk * n_chunks)
+    outs = {}
+    for name, prec in (("c8", pk.PREC_FP16C8), ("r", pk.PREC_FP16R)):
+        am = pk.AcousticModel(ctx, prec).from_layers(layers, prior, 5, 5)
+        st = pk.Stream(ctx, am, S, chunk, g, 0.1)
+        got = [st.push(pcm[:, k * chunk:(k + 1) * chunk].copy()) for k in range(n_chunks)]
+        got.append(st.flush())
+        outs[name] = [np.concatenate([np.asarray(o[s]).copy() for o in got]) for s in range(S)]
+        st.close()
+        am.close()
+    for a, b in zip(outs["c8"], outs["r"]):
+        assert a.shape == b.shape and a.shape[0] > 0
+        assert np.array_equal(a, b)

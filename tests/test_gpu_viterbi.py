@@ -82,7 +82,7 @@ def test_toy_model_words_match_the_reference(ctx, golden, toy_conf):
     buf = sym[16 + 4 * n:]
     words = [buf[i:buf.index(b"\0", i)].decode() for i in idx]
     pcms = [golden["hello_pcm"], golden["cat_pcm"], golden["hello_pcm"]]
-    for prec in (pk.PREC_BF16X3, pk.PREC_FP16C8):
+    for prec in (pk.PREC_BF16X3, pk.PREC_FP16C8, pk.PREC_FP16R):
         hyps, wts, frames = gpu_decode(ctx, toy_conf, pcms, golden["cmvn_stats"], prec)
         for name, h, w, T in zip(("hello", "cat", "hello"), hyps, wts, frames):
             assert words_of(h, words) == gold[name][0], (name, h)

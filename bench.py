@@ -337,7 +337,8 @@ def measure_batch(env, cfg, precision, n_utts, steps, warmup, sample_clocks):
             t = json.load(open(tpath))
             key = "config%s_%s" % (cfg["key"], precision)
             if key in t:
-                traffic = t[key]["dram_bytes_per_frame"] * frames / (cfg["hidden"] + 1)
+                # per launch, like `achieved` (FP16R: 2 x (hidden + 1) launches per step)
+                traffic = t[key]["dram_bytes_per_frame"] * frames / max(gemm_launches / max(steps, 1), 1)
                 traffic_src = "static: %s of profiles/r2_gemm_traffic.json (ncu --set full, " \
                               "dram__bytes_read+write summed over the GEMM launches of one step, " \
                               "scaled by frames; not measured in this run)" % key

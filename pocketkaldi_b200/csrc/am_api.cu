@@ -901,6 +901,9 @@ int pkb_batch_decode(pkb_batch_t *b, const pkb_fst_t *fst, float beam, int max_t
   PKB_REQUIRE(fst->max_ilabel < static_cast<int>(b->am->tid2pdf.size()),
               "pkb_batch_decode: the graph uses input label %d but the model's tid2pdf map has %zu entries",
               fst->max_ilabel, b->am->tid2pdf.size());
+  for (int32_t v : b->am->tid2pdf)
+    PKB_REQUIRE(v >= 0 && v < b->am->num_pdfs, "pkb_batch_decode: tid2pdf entry %d outside [0, %d)", v,
+                b->am->num_pdfs);
   PKB_REQUIRE(max_words > 0 && words_out && n_words_out && weight_out, "pkb_batch_decode: bad output arguments");
   Ctx *c = b->c;
   PKB_CUDA(cudaSetDevice(c->device));

@@ -420,7 +420,7 @@ viterbi_kernel(FstDev fst, float beam, int max_tok, uint32_t mask, int max_log, 
 constexpr uint32_t kInactive = 0xffffffffu;
 
 template <int kArcsPerThread>
-__global__ void __launch_bounds__(kVitThreads)
+__global__ void __launch_bounds__(kVitThreads, kArcsPerThread <= 8 ? 3 : 1)
 viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_words,
                      const float *__restrict__ loglik, int num_pdfs, const int64_t *__restrict__ row_off,
                      const int32_t *__restrict__ num_frames, int n_utts, const int32_t *__restrict__ tid2pdf,
@@ -441,26 +441,72 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
   int *log_prev = reinterpret_cast<int *>(work_base + static_cast<size_t>(blockIdx.x) * work_stride);
   int *log_ol = log_prev + max_log;
   const int tid = threadIdx.x;
+  // acoustic costs of the frame, one slot per DISTINCT pdf the graph's arcs read (a word-loop
+  // graph reads each pdf from ~15 arcs): bit set of used pdfs, its per-word prefix counts, the pdf
+  // of every slot and two frames of costs
+  const int W = (num_pdfs + 31) >> 5;
+  const int Dmax = min(num_arcs, num_pdfs);
+  uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_dense) + 6 * S;
+  int *s_wpre = reinterpret_cast<int *>(s_bits + W);
+  int *s_pdf = s_wpre + W;
+  float *s_ll = reinterpret_cast<float *>(s_pdf + Dmax);  // [2][Dmax]
+  __shared__ int s_D;
 
   // this thread's arcs (the same in every pass of every frame)
-  int a_src[kArcsPerThread], a_dst[kArcsPerThread], a_il[kArcsPerThread];
+  // source | destination << 16 (at most 2048 states; source 0xffff: no arc), weight, and the pdf
+  // of an emitting arc (-1: epsilon arc)
+  uint32_t a_sd[kArcsPerThread];
   float a_w[kArcsPerThread];
+  int a_pdf[kArcsPerThread];
 #pragma unroll
   for (int k = 0; k < kArcsPerThread; ++k) {
     const int a = tid + k * kVitThreads;
     const bool ok = a < num_arcs;
-    a_src[k] = ok ? __ldg(&fst.arc_src[a]) : -1;
-    a_dst[k] = ok ? __ldg(&fst.arc_dst[a]) : 0;
-    a_il[k] = ok ? __ldg(&fst.arc_il[a]) : 0;
+    a_sd[k] = ok ? (static_cast<uint32_t>(__ldg(&fst.arc_src[a])) | (static_cast<uint32_t>(__ldg(&fst.arc_dst[a])) << 16))
+                 : 0xffffu;
     a_w[k] = ok ? __ldg(&fst.arc_w[a]) : 0.0f;
+    const int il = ok ? __ldg(&fst.arc_il[a]) : 0;
+    a_pdf[k] = (ok && il != 0) ? __ldg(&tid2pdf[il]) : -1;
   }
-  // pdf of every emitting arc: the acoustic cost of the NEXT frame is loaded while the current one
-  // is searched (which pdfs an arc reads does not depend on the tokens), so the row's DRAM latency
-  // is off the critical path of the frame step
-  int a_pdf[kArcsPerThread];
+  auto src_of = [&](int k) { return static_cast<int>(a_sd[k] & 0xffffu); };
+  auto dst_of = [&](int k) { return static_cast<int>(a_sd[k] >> 16); };
+  auto has_arc = [&](int k) { return (a_sd[k] & 0xffffu) != 0xffffu; };
+  // slots of the distinct pdfs; a_pdf[k] becomes the slot of arc k's pdf
+  for (int w = tid; w < W; w += kVitThreads) s_bits[w] = 0u;
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < kArcsPerThread; ++k)
-    a_pdf[k] = (a_src[k] >= 0 && a_il[k] != 0) ? __ldg(&tid2pdf[a_il[k]]) : -1;
+    if (a_pdf[k] >= 0) atomicOr(&s_bits[a_pdf[k] >> 5], 1u << (a_pdf[k] & 31));
+  __syncthreads();
+  if (tid < 32) {
+    int running = 0;
+    for (int base = 0; base < W; base += 32) {
+      const int w = base + tid;
+      const int cnt = w < W ? __popc(s_bits[w]) : 0;
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tid >= o) inc += t;
+      }
+      if (w < W) s_wpre[w] = running + inc - cnt;
+      running += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (tid == 0) s_D = running;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kArcsPerThread; ++k) {
+    if (a_pdf[k] < 0) continue;
+    const int pdf = a_pdf[k];
+    const int slot = s_wpre[pdf >> 5] + __popc(s_bits[pdf >> 5] & ((1u << (pdf & 31)) - 1u));
+    s_pdf[slot] = pdf;  // every arc of the pdf writes the same value
+    a_pdf[k] = slot;
+  }
+  __syncthreads();
+  const int D = s_D;
+  // The acoustic costs of the NEXT frame are loaded (one load per distinct pdf) while the current
+  // frame is searched: the row's DRAM latency is off the critical path of the frame step.
 
   // epsilon closure of frame table c under `cutoff`, winners, word back-pointers
   auto finish_frame = [&](int c, int p, double cutoff, const double (&td)[kArcsPerThread], const bool (&live)[kArcsPerThread]) {
@@ -470,13 +516,13 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kArcsPerThread; ++k) {
-          if (a_src[k] < 0 || a_il[k] != 0) continue;
-          const uint32_t cs = *reinterpret_cast<volatile uint32_t *>(&cost[c][a_src[k]]);
+          if (!has_arc(k) || a_pdf[k] >= 0) continue;
+          const uint32_t cs = *reinterpret_cast<volatile uint32_t *>(&cost[c][src_of(k)]);
           if (cs == kInactive) continue;
           const double total = static_cast<double>(unord32(cs)) + static_cast<double>(a_w[k]);
           if (total > cutoff) continue;
           const uint32_t o = ord32(static_cast<float>(total));
-          if (atomicMin(&cost[c][a_dst[k]], o) > o) s_changed = 1;
+          if (atomicMin(&cost[c][dst_of(k)], o) > o) s_changed = 1;
         }
         __syncthreads();
         const int changed = s_changed;  // read by everyone before thread 0 resets it
@@ -488,16 +534,16 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
     // arcs from their source's final cost
 #pragma unroll
     for (int k = 0; k < kArcsPerThread; ++k) {
-      if (a_src[k] < 0) continue;
+      if (!has_arc(k)) continue;
       const uint32_t a = static_cast<uint32_t>(tid + k * kVitThreads);
-      if (a_il[k] != 0) {
-        if (live[k] && ord32(static_cast<float>(td[k])) == cost[c][a_dst[k]]) atomicMin(&warc[c][a_dst[k]], a);
+      if (a_pdf[k] >= 0) {
+        if (live[k] && ord32(static_cast<float>(td[k])) == cost[c][dst_of(k)]) atomicMin(&warc[c][dst_of(k)], a);
       } else if (fst.has_eps) {
-        const uint32_t cs = cost[c][a_src[k]];
+        const uint32_t cs = cost[c][src_of(k)];
         if (cs == kInactive) continue;
         const double total = static_cast<double>(unord32(cs)) + static_cast<double>(a_w[k]);
-        if (total <= cutoff && ord32(static_cast<float>(total)) == cost[c][a_dst[k]])
-          atomicMin(&warc[c][a_dst[k]], a | 0x80000000u);
+        if (total <= cutoff && ord32(static_cast<float>(total)) == cost[c][dst_of(k)])
+          atomicMin(&warc[c][dst_of(k)], a | 0x80000000u);
       }
     }
     __syncthreads();
@@ -572,6 +618,8 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
     // ---- InitDecoding (src/decoder.cc:82-101)
     int cur = 0;
     if (tid == 0) cost[0][fst.start] = ord32(0.0f);
+    if (T > 0)
+      for (int d = tid; d < D; d += kVitThreads) s_ll[d] = __ldg(&ll0[s_pdf[d]]);
     __syncthreads();
     {
       double td[kArcsPerThread];
@@ -582,19 +630,17 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
       end_frame(0, 1);
     }
     bool alive = true;
-    float ac_next[kArcsPerThread];
-#pragma unroll
-    for (int k = 0; k < kArcsPerThread; ++k) ac_next[k] = (T > 0 && a_pdf[k] >= 0) ? __ldg(&ll0[a_pdf[k]]) : 0.0f;
     for (int f = 0; f < T && alive && !s_err; ++f) {
       const int prev = cur;
       cur ^= 1;
-      float ac_cur[kArcsPerThread];
+      const float *ll_cur = s_ll + (f & 1) * Dmax;
+      float ll_next[kArcsPerThread];  // D <= num_arcs <= kArcsPerThread * kVitThreads
       {
         const float *lln = ll0 + static_cast<int64_t>(f + 1) * num_pdfs;
 #pragma unroll
         for (int k = 0; k < kArcsPerThread; ++k) {
-          ac_cur[k] = ac_next[k];
-          if (f + 1 < T && a_pdf[k] >= 0) ac_next[k] = __ldg(&lln[a_pdf[k]]);
+          const int d = tid + k * kVitThreads;
+          ll_next[k] = (f + 1 < T && d < D) ? __ldg(&lln[s_pdf[d]]) : 0.0f;
         }
       }
       // ---- GetCutoff below kBeamSize tokens: the best cost was reduced when the table was finished
@@ -609,12 +655,12 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
         for (int k = 0; k < kArcsPerThread; ++k) {
           live[k] = false;
           td[k] = 0.0;
-          if (a_src[k] < 0 || a_il[k] == 0) continue;
-          const uint32_t cs = cost[prev][a_src[k]];
+          if (a_pdf[k] < 0) continue;
+          const uint32_t cs = cost[prev][src_of(k)];
           if (cs == kInactive) continue;
           const float c = unord32(cs);
           if (c > weight_cutoff) continue;
-          const float ac = -ac_cur[k];
+          const float ac = -ll_cur[a_pdf[k]];
           td[k] = static_cast<double>(c) + static_cast<double>(a_w[k]) + static_cast<double>(ac);
           live[k] = true;
           m = min(m, ord64(td[k]));
@@ -630,10 +676,18 @@ viterbi_dense_kernel(FstDev fst, int num_arcs, float beam, int max_log, int max_
 #pragma unroll
       for (int k = 0; k < kArcsPerThread; ++k) {
         live[k] = live[k] && td[k] <= next_cutoff;
-        if (live[k]) atomicMin(&cost[cur][a_dst[k]], ord32(static_cast<float>(td[k])));
+        if (live[k]) atomicMin(&cost[cur][dst_of(k)], ord32(static_cast<float>(td[k])));
       }
       __syncthreads();
       finish_frame(cur, prev, static_cast<double>(static_cast<float>(next_cutoff)), td, live);
+      {
+        float *ll_nx = s_ll + ((f + 1) & 1) * Dmax;  // last read two frames ago
+#pragma unroll
+        for (int k = 0; k < kArcsPerThread; ++k) {
+          const int d = tid + k * kVitThreads;
+          if (d < D) ll_nx[d] = ll_next[k];
+        }
+      }
       end_frame(cur, prev);
     }
 
@@ -783,9 +837,13 @@ int launch_viterbi(Ctx *c, const pkb_fst *fst, const ViterbiConfig &cfg, const f
   if (fst->num_states <= 2048 && fst->num_arcs <= 16 * kVitThreads && !(env_dense && atoi(env_dense) == 0)) {
     // dense kernel: no token capacity to run out of; the global workspace holds the word records only
     const size_t stride = (2 * sizeof(int) * static_cast<size_t>(cfg.max_log) + 255) & ~static_cast<size_t>(255);
+    // one resident wave at most (the workspace is per block); the kernels are built for three
+    // blocks per SM up to eight arcs per thread
     const int grid = std::min(n_utts, c->sm_count * 4);
     PKB_TRY(work->ensure(stride * grid));
-    const size_t smem = 6 * sizeof(uint32_t) * static_cast<size_t>(fst->num_states);
+    const size_t smem = sizeof(uint32_t) * (6 * static_cast<size_t>(fst->num_states) +
+                                            2 * static_cast<size_t>((num_pdfs + 31) / 32) +
+                                            3 * static_cast<size_t>(std::min(fst->num_arcs, num_pdfs)));
     LaunchScope scope(c, PKB_KERNEL_MISC);
 #define PKB_VIT_DENSE(APT)                                                                               \
   do {                                                                                                   \

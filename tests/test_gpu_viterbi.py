@@ -178,3 +178,24 @@ def test_capacity_overflow_is_reported_not_silent(ctx, tmp_path):
     assert hyps[0] is None and hyps[1] is None  # hundreds of live states do not fit 64 tokens: flagged
     hyps, _, _ = gpu_decode(ctx, conf, pcms, g, max_tokens=1024)
     assert all(h is not None and len(h) > 0 for h in hyps)   # and the workspace is clean afterwards
+
+
+def test_tid2pdf_outside_the_model_is_rejected(ctx):
+    # the reference would index past the log-likelihood row (src/decodable.cc:24-31); here the
+    # decode call reports it
+    import tools.decode_demo as demo
+    P = 64
+    layers = formats.make_dnn(np.random.default_rng(8), 440, 32, 1, P)
+    graph, tid2pdf = demo.word_loop_graph(4, 3, P)
+    bad = np.asarray(tid2pdf, np.int32).copy()
+    bad[-1] = P  # one past the last pdf
+    am = pk.AcousticModel(ctx, pk.PREC_BF16X3).from_layers(layers, np.full(P, 1.0 / P, np.float32), 5, 5, tid2pdf=bad)
+    fst = pk.Fst(ctx, graph=graph)
+    b = pk.Batch(ctx, [16000], synth_global_cmvn(), am, prob_scale=0.1)
+    b.synth_pcm(1, 0)
+    b.run(pk.STAGE_ALL)
+    with pytest.raises(pk.PkbError):
+        b.decode(fst)
+    b.close()
+    fst.close()
+    am.close()
